@@ -1,0 +1,143 @@
+/*
+ * micformer_b200 -- C ABI of the B200 (sm_100a) kernels behind the MicFormer dual-stream hot path.
+ *
+ * The reference (fxxJuses/MICFormer) is pure PyTorch: it has NO FFI / plugin interface for this path
+ * (SURVEY.md §8b).  The boundary a maintainer binds is therefore the set of ATen calls its Python makes;
+ * every entry point below names the reference lines (relative to /root/reference/MicFormer) it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - all tensors are contiguous fp32 device pointers owned by the caller (torch's allocator); the library
+ *     never allocates, never retains pointers and never synchronises; everything is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph capturable.
+ *   - activations are channels-last token grids (B, D, H, W, C); "rows" means the flattened (B*D*H*W) axis.
+ *   - return value 0 = success, negative = error (mic_last_error_string() gives the reason, thread-local).
+ *     Nothing throws or exits across the ABI.
+ *   - "+=" outputs are accumulated atomically into caller-initialised buffers.
+ */
+#ifndef MICFORMER_B200_H
+#define MICFORMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIC_OK 0
+#define MIC_ERR_INVALID (-1)
+#define MIC_ERR_UNSUPPORTED (-2)
+#define MIC_ERR_CUDA (-3)
+
+int mic_version(void);
+const char* mic_last_error_string(void);
+/* number of kernel launches issued by this library in the calling process since load / last reset */
+int64_t mic_launch_count(void);
+void mic_reset_launch_count(void);
+/* 0 = fp32 CUDA-core GEMMs (exact parity path), 1 = tcgen05 TF32 tensor-core GEMMs where shapes allow,
+ * 2 = tcgen05 3xTF32 split (fp32-faithful) */
+int mic_set_gemm_mode(int mode);
+int mic_get_gemm_mode(void);
+
+/* ---- LayerNorm over the channel axis (nn.LayerNorm eps=1e-5; models/MICFormer_self.py:343,477,404,559,578,
+ *      1011-1012,1034 and LayerNormProxy :263-273).  The input may be the channel-concatenation of two
+ *      tensors (x0:C0 | x1:C1) -- this is `torch.cat([moving, fixed], -1)` + norm2 (:1033-1034) without the
+ *      cat.  The output may be zero-padded on the trailing side of D/H/W to (Dp,Hp,Wp) -- this is F.pad after
+ *      norm1 (:343-350, :477-483).  mean/rstd are saved per un-padded row for the backward. */
+int mic_layernorm_fwd(const float* x0, int C0, const float* x1, int C1, const float* gamma, const float* beta,
+                      float* y, float* mean, float* rstd, int B, int D, int H, int W, int Dp, int Hp, int Wp,
+                      float eps, void* stream);
+/* dx0 = (dres0 ? dres0 : 0) + LN'(dy) (same for dx1); dgamma/dbeta += column sums. dy is in the padded layout. */
+int mic_layernorm_bwd(const float* dy, const float* x0, int C0, const float* x1, int C1, const float* gamma,
+                      const float* mean, const float* rstd, const float* dres0, const float* dres1, float* dx0,
+                      float* dx1, float* dgamma, float* dbeta, int B, int D, int H, int W, int Dp, int Hp, int Wp,
+                      void* stream);
+
+/* ---- Linear layers (F.linear: q/kv/proj :188-201,:246-259; Mlp fc1/fc2 :28-34; concat_back_dim :1029-1030;
+ *      stride==kernel convs as GEMMs :557,:576,:871,:1037).
+ *      Y[M,N] = epi(X[M,K] @ Wm + bias[N]);  w_is_kn=0: Wm = W[N,K]^T (nn.Linear / Conv weights),
+ *      w_is_kn=1: Wm = W[K,N] (ConvTranspose weights).  epi: act=1 -> pre (if non-null) receives the
+ *      pre-activation and Y = gelu_erf(pre) (:30);  res != null -> Y = res + rowscale[m / rows_per_sample] * val
+ *      (residual add :419,:424 with timm DropPath per-sample scale; rowscale null -> 1);
+ *      accumulate=1 -> Y += val (two-source linear == Linear on cat[a,b] :1027-1030). */
+int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn, const float* bias, float* Y, int ldy,
+                   int M, int N, int K, int act, float* pre, int ldpre, const float* res, int ldres,
+                   const float* rowscale, int rows_per_sample, int accumulate, void* stream);
+/* dX[M,K] = (rowscale * dY[M,N]) @ Wm^T, optionally * gelu'(gelu_pre[M,K]); accumulate=1 -> dX += */
+int mic_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int w_is_kn, float* dX, int lddx, int M,
+                        int N, int K, const float* gelu_pre, int ldpre, const float* rowscale, int rows_per_sample,
+                        int accumulate, void* stream);
+/* dW += (rowscale * dY)^T @ X  (shape [N,K], or [K,N] if w_is_kn);  db[N] += column sums of rowscale*dY (nullable) */
+int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int w_is_kn,
+                          float* db, int M, int N, int K, const float* rowscale, int rows_per_sample, void* stream);
+
+/* ---- Windowed multi-head attention core: window_partition + softmax(q k^T * scale) v + window_reverse
+ *      (:37-50,:117-132,:193-200,:251-258) without materialising windows or scores.  q/k/v/out are token-grid
+ *      tensors (B,Dp,Hp,Wp,heads*hd) with row strides ldq/ldkv/ldo (k and v usually point into one kv buffer);
+ *      lse (rows, heads) is saved for the backward.  No mask, no relative-position bias. */
+int mic_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo,
+                        float* lse, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh, int ww,
+                        float scale, void* stream);
+int mic_window_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* out,
+                        const float* dout, int ldo, const float* lse, float* dq, int lddq, float* dk, float* dv,
+                        int lddkv, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh, int ww,
+                        float scale, void* stream);
+
+/* ---- 3x3x3 convolution, stride 1, zero padding 1, channels-last, up to two concatenated input tensors
+ *      (conv_offset[0] on cat[LN(x), xa] :313-314,:354-356; out_conv :1046,:1053).  Inputs live on the
+ *      (D,H,W) grid and are implicitly zero outside it; outputs are produced on (Dp,Hp,Wp) >= (D,H,W).
+ *      Wt is the weight permuted to [27][C0+C1][Co]; Co <= 16.  out_ncdhw=1 writes (B,Co,Dp,Hp,Wp). */
+int mic_conv3_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wt, const float* bias, float* y,
+                  int B, int D, int H, int W, int Dp, int Hp, int Wp, int Co, int out_ncdhw, void* stream);
+int mic_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1, int acc1,
+                       int B, int D, int H, int W, int Dp, int Hp, int Wp, int Co, int dy_ncdhw, void* stream);
+/* dWt[27][C0+C1][Co] += ..., dbias[Co] += ... */
+int mic_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
+                         int B, int D, int H, int W, int Dp, int Hp, int Wp, int Co, int dy_ncdhw, void* stream);
+
+/* ---- Offset head: LayerNormProxy(16) -> GELU -> Conv3d(16->3,k1,no bias) -> + reference points
+ *      (:315-317, :326-337, :360-364).  h (P,HC) -> pos (P,3) with P = B*Dp*Hp*Wp. */
+int mic_offset_head_fwd(const float* h, const float* gamma, const float* beta, const float* w3, float* pos, int B,
+                        int Dp, int Hp, int Wp, int HC, float eps, void* stream);
+int mic_offset_head_bwd(const float* dpos, const float* h, const float* gamma, const float* beta, const float* w3,
+                        float* dh, float* dgamma, float* dbeta, float* dw3, int B, int Dp, int Hp, int Wp, int HC,
+                        float eps, void* stream);
+
+/* ---- Deformable trilinear resampling == SpatialTransformer.forward (models/STN.py:9-32) on the zero-padded
+ *      other-modality map (:350,:379): out[p] = trilinear(src, c) with c_i = (idx_i + pos_i) * S_i/(S_i-1) - 0.5,
+ *      S = (Dp,Hp,Wp), zeros outside.  src lives on (D,H,W) (implicit zero pad up to (Dp,Hp,Wp)). */
+int mic_deform_sample_fwd(const float* src, const float* pos, float* out, int B, int D, int H, int W, int Dp, int Hp,
+                          int Wp, int C, void* stream);
+/* dsrc += scatter (atomic), dpos = gradient w.r.t. pos (written) */
+int mic_deform_sample_bwd(const float* dout, const float* src, const float* pos, float* dsrc, float* dpos, int B,
+                          int D, int H, int W, int Dp, int Hp, int Wp, int C, void* stream);
+
+/* ---- k^3 block <-> row permutation for the stride==kernel (transposed) convolutions: PatchEmbed3D :871,
+ *      PatchMerging :557, PatchExpand :576, reverse_patch_embedding :1037.  grid (B, k*D', k*H', k*W', C)
+ *      channels-last <-> rows (B*D'*H'*W', k^3*C) with column order (kz,ky,kx,c).  to_rows=1 packs, 0 unpacks.
+ *      grid_batch_stride (floats) lets a single-channel NCDHW volume be read in place (C=1). */
+int mic_block_permute(const float* src, float* dst, int B, int Dq, int Hq, int Wq, int k, int C,
+                      int64_t grid_batch_stride, int to_rows, void* stream);
+
+/* ---- MDiceLoss (loss/dice.py:130-166): per channel sigmoid -> sum p*t, sum p^2, sum t^2, sum BCE (log clamped
+ *      at -100) in one pass; finalize -> loss = (0.7*sum_c dice_c + 0.3*sum_c bce_c)/C and the per-channel
+ *      coefficients the backward needs.  sums: double[C*4] zeroed by the caller (and, for a global-batch loss
+ *      under data parallelism, all-reduced between the two calls).  n_per_channel = B*S (global). */
+int mic_dice_bce_partial(const float* logits, const float* target, double* sums, int B, int C, int64_t S, void* stream);
+int mic_dice_bce_finalize(const double* sums, float* loss, float* coef /*[C*3]*/, int C, double n_per_channel,
+                          void* stream);
+int mic_dice_bce_bwd(const float* logits, const float* target, const float* coef, const float* dloss, float* dlogits,
+                     int B, int C, int64_t S, double n_per_channel, void* stream);
+
+/* ---- small utilities: y = a + rowscale*b with crop from a padded grid (residual after window_reverse + crop
+ *      :397-400,:419), fill, axpy ---- */
+int mic_crop_residual(const float* res, const float* branch, const float* rowscale, float* y, int B, int D, int H,
+                      int W, int Dp, int Hp, int Wp, int C, void* stream);
+/* dbranch (padded grid) = rowscale * dy inside, 0 in the pad */
+int mic_crop_residual_bwd(const float* dy, const float* rowscale, float* dbranch, int B, int D, int H, int W, int Dp,
+                          int Hp, int Wp, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICFORMER_B200_H */

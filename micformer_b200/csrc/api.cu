@@ -1,0 +1,99 @@
+// C-ABI glue: error string, launch counter, GEMM-mode switch and the entry points that dispatch between the
+// exact fp32 CUDA-core kernels and the tcgen05 tensor-core kernels.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace mic {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_gemm_mode{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// gemm_simt.cu
+int simt_linear_fwd(const float*, int, const float*, int, int, const float*, float*, int, int, int, int, int, float*, int,
+                    const float*, int, const float*, int, int, cudaStream_t);
+int simt_linear_bwd_data(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, int,
+                         const float*, int, int, cudaStream_t);
+int simt_linear_bwd_weight(const float*, int, const float*, int, float*, int, int, float*, int, int, int, const float*, int,
+                           cudaStream_t);
+// gemm_tc.cu (tcgen05); return MIC_ERR_UNSUPPORTED when the shape is not taken
+int tc_linear_fwd(const float*, int, const float*, int, int, const float*, float*, int, int, int, int, int, float*, int,
+                  const float*, int, const float*, int, int, int, cudaStream_t);
+// window_attn.cu
+int simt_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int,
+                         int, int, int, int, float, cudaStream_t);
+int simt_window_attn_bwd(const float*, int, const float*, const float*, int, const float*, const float*, int, const float*,
+                         float*, int, float*, float*, int, int, int, int, int, int, int, int, int, int, float,
+                         cudaStream_t);
+
+}  // namespace mic
+
+using namespace mic;
+
+extern "C" int mic_version(void) { return 100; }
+extern "C" const char* mic_last_error_string(void) { return g_err; }
+extern "C" int64_t mic_launch_count(void) { return g_launches.load(); }
+extern "C" void mic_reset_launch_count(void) { g_launches.store(0); }
+extern "C" int mic_set_gemm_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(MIC_ERR_INVALID, "gemm mode %d not in {0,1,2}", mode);
+    g_gemm_mode.store(mode);
+    return MIC_OK;
+}
+extern "C" int mic_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
+extern "C" int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn, const float* bias, float* Y,
+                              int ldy, int M, int N, int K, int act, float* pre, int ldpre, const float* res, int ldres,
+                              const float* rowscale, int rows_per_sample, int accumulate, void* stream) {
+    MIC_REQUIRE(X && W && Y && M > 0 && N > 0 && K > 0, "linear_fwd: bad arguments (M=%d N=%d K=%d)", M, N, K);
+    MIC_REQUIRE(!(accumulate && (act || res)), "linear_fwd: accumulate cannot be combined with act/res");
+    const int mode = g_gemm_mode.load();
+    if (mode > 0) {
+        int rc = tc_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
+                               rows_per_sample, accumulate, mode, (cudaStream_t)stream);
+        if (rc != MIC_ERR_UNSUPPORTED) return rc;
+    }
+    return simt_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
+                           rows_per_sample, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int mic_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int w_is_kn, float* dX, int lddx,
+                                   int M, int N, int K, const float* gelu_pre, int ldpre, const float* rowscale,
+                                   int rows_per_sample, int accumulate, void* stream) {
+    MIC_REQUIRE(dY && W && dX && M > 0 && N > 0 && K > 0, "linear_bwd_data: bad arguments");
+    return simt_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
+                                accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int w_is_kn,
+                                     float* db, int M, int N, int K, const float* rowscale, int rows_per_sample,
+                                     void* stream) {
+    MIC_REQUIRE(dY && X && dW && M > 0 && N > 0 && K > 0, "linear_bwd_weight: bad arguments");
+    return simt_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int mic_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo,
+                                   float* lse, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh, int ww,
+                                   float scale, void* stream) {
+    MIC_REQUIRE(q && k && v && out && lse, "window_attn_fwd: null pointer");
+    return simt_window_attn_fwd(q, ldq, k, v, ldkv, out, ldo, lse, B, Dp, Hp, Wp, heads, hd, wd, wh, ww, scale,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int mic_window_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* out,
+                                   const float* dout, int ldo, const float* lse, float* dq, int lddq, float* dk,
+                                   float* dv, int lddkv, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh,
+                                   int ww, float scale, void* stream) {
+    MIC_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv, "window_attn_bwd: null pointer");
+    return simt_window_attn_bwd(q, ldq, k, v, ldkv, out, dout, ldo, lse, dq, lddq, dk, dv, lddkv, B, Dp, Hp, Wp, heads, hd,
+                                wd, wh, ww, scale, (cudaStream_t)stream);
+}

@@ -1,0 +1,626 @@
+"""Host-side operators: ``torch.autograd.Function``s that sequence the sm_100a kernels of the C ABI.
+
+torch is plumbing here (device memory from its caching allocator, the current stream, autograd's tape for
+ordering); every arithmetic step of the hot path is one of the ``mic_*`` kernels.  Nothing in this file has a
+CPU or torch-op fallback.
+
+Layout: activations are channels-last token grids ``(B, D, H, W, C)`` fp32 contiguous.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _native as N
+
+LN_EPS = 1e-5
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------------------
+# geometry
+# ----------------------------------------------------------------------------------------------------------
+def window_geometry(dims: Sequence[int], window: Sequence[int]):
+    """(use_window, padded dims) -- get_window_size clamp (reference M:135-145) + trailing pad (M:345-348)."""
+    ws = tuple(d if d <= w else w for d, w in zip(dims, window))
+    pdims = tuple(d + (w - d % w) % w for d, w in zip(dims, ws))
+    return ws, pdims
+
+
+def _empty(shape, like: Tensor) -> Tensor:
+    return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+
+def _zeros(shape, like: Tensor) -> Tensor:
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# thin kernel wrappers (no autograd)
+# ----------------------------------------------------------------------------------------------------------
+def ln_fwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, beta: Tensor, dims, pdims=None):
+    """x0 (B,D,H,W,C0) [| x1 (B,D,H,W,C1)] -> y (B,Dp,Hp,Wp,C0+C1) zero padded, mean, rstd (rows)."""
+    B, D, H, W = dims
+    Dp, Hp, Wp = pdims if pdims is not None else (D, H, W)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    y = _empty((B, Dp, Hp, Wp, C0 + C1), x0)
+    mean = _empty((B * D * H * W,), x0)
+    rstd = _empty((B * D * H * W,), x0)
+    N.call("mic_layernorm_fwd", N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(gamma), N.ptr(beta), N.ptr(y), N.ptr(mean),
+           N.ptr(rstd), B, D, H, W, Dp, Hp, Wp, LN_EPS)
+    return y, mean, rstd
+
+
+def ln_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
+           dres0: Optional[Tensor], dres1: Optional[Tensor], dims, pdims=None):
+    B, D, H, W = dims
+    Dp, Hp, Wp = pdims if pdims is not None else (D, H, W)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    dx0 = torch.empty_like(x0)
+    dx1 = torch.empty_like(x1) if x1 is not None else None
+    dgamma = _zeros((C0 + C1,), x0)
+    dbeta = _zeros((C0 + C1,), x0)
+    N.call("mic_layernorm_bwd", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(gamma), N.ptr(mean), N.ptr(rstd),
+           N.ptr(dres0), N.ptr(dres1), N.ptr(dx0), N.ptr(dx1), N.ptr(dgamma), N.ptr(dbeta), B, D, H, W, Dp, Hp, Wp)
+    return dx0, dx1, dgamma, dbeta
+
+
+def _view_ptr(t: Tensor, col: int) -> int:
+    """pointer to column ``col`` of a 2-D row-major buffer"""
+    return t.data_ptr() + 4 * col
+
+
+def linear_fwd(X: Tensor, ldx: int, W: Tensor, bias: Optional[Tensor], M: int, Nout: int, K: int, *, out: Tensor = None,
+               out_col: int = 0, ldy: int = None, w_is_kn: bool = False, ldw: int = None, w_col: int = 0, x_col: int = 0,
+               act: bool = False, pre: Tensor = None, res: Tensor = None, rowscale: Tensor = None, rps: int = 0,
+               accumulate: bool = False):
+    if out is None:
+        out = _empty((M, Nout), X)
+        ldy = Nout
+    if ldw is None:
+        ldw = Nout if w_is_kn else K
+    N.call("mic_linear_fwd", _view_ptr(X, x_col), ldx, _view_ptr(W, w_col), ldw, int(w_is_kn), N.ptr(bias),
+           _view_ptr(out, out_col), ldy, M, Nout, K, int(act), N.ptr(pre), Nout, N.ptr(res), Nout, N.ptr(rowscale), rps,
+           int(accumulate))
+    return out
+
+
+def linear_bwd_data(dY: Tensor, lddy: int, W: Tensor, M: int, Nout: int, K: int, *, dy_col: int = 0, out: Tensor = None,
+                    out_col: int = 0, lddx: int = None, w_is_kn: bool = False, ldw: int = None, w_col: int = 0,
+                    gelu_pre: Tensor = None, rowscale: Tensor = None, rps: int = 0, accumulate: bool = False):
+    if out is None:
+        out = _empty((M, K), dY)
+        lddx = K
+    if ldw is None:
+        ldw = Nout if w_is_kn else K
+    N.call("mic_linear_bwd_data", _view_ptr(dY, dy_col), lddy, _view_ptr(W, w_col), ldw, int(w_is_kn),
+           _view_ptr(out, out_col), lddx, M, Nout, K, N.ptr(gelu_pre), K, N.ptr(rowscale), rps, int(accumulate))
+    return out
+
+
+def linear_bwd_weight(dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: int, K: int, *, dy_col: int = 0,
+                      x_col: int = 0, w_is_kn: bool = False, dW: Tensor = None, lddw: int = None, dw_col: int = 0,
+                      want_bias: bool = True, db: Tensor = None, rowscale: Tensor = None, rps: int = 0):
+    """Returns (dW, db); dW/db are accumulated into when passed in."""
+    if dW is None:
+        dW = _zeros((K, Nout) if w_is_kn else (Nout, K), dY)
+        lddw = Nout if w_is_kn else K
+    if db is None and want_bias:
+        db = _zeros((Nout,), dY)
+    N.call("mic_linear_bwd_weight", _view_ptr(dY, dy_col), lddy, _view_ptr(X, x_col), ldx, _view_ptr(dW, dw_col), lddw,
+           int(w_is_kn), N.ptr(db) if want_bias else None, M, Nout, K, N.ptr(rowscale), rps)
+    return dW, db
+
+
+def window_attn_fwd(qkv: Tensor, C: int, heads: int, B: int, pdims, ws):
+    """qkv (P, 3C) rows on the padded grid -> o (P, C), lse (P, heads)."""
+    Dp, Hp, Wp = pdims
+    P = B * Dp * Hp * Wp
+    hd = C // heads
+    o = _empty((P, C), qkv)
+    lse = _empty((P, heads), qkv)
+    N.call("mic_window_attn_fwd", _view_ptr(qkv, 0), 3 * C, _view_ptr(qkv, C), _view_ptr(qkv, 2 * C), 3 * C, N.ptr(o), C,
+           N.ptr(lse), B, Dp, Hp, Wp, heads, hd, ws[0], ws[1], ws[2], float(hd) ** -0.5)
+    return o, lse
+
+
+def window_attn_bwd(qkv: Tensor, o: Tensor, do: Tensor, lse: Tensor, C: int, heads: int, B: int, pdims, ws):
+    Dp, Hp, Wp = pdims
+    hd = C // heads
+    dqkv = torch.empty_like(qkv)
+    N.call("mic_window_attn_bwd", _view_ptr(qkv, 0), 3 * C, _view_ptr(qkv, C), _view_ptr(qkv, 2 * C), 3 * C, N.ptr(o),
+           N.ptr(do), C, N.ptr(lse), _view_ptr(dqkv, 0), 3 * C, _view_ptr(dqkv, C), _view_ptr(dqkv, 2 * C), 3 * C, B, Dp, Hp,
+           Wp, heads, hd, ws[0], ws[1], ws[2], float(hd) ** -0.5)
+    return dqkv
+
+
+def pad_grid(x: Tensor, dims, pdims) -> Tensor:
+    """zero-pad (B,D,H,W,C) -> (B,Dp,Hp,Wp,C)  (F.pad of xa, reference M:350)"""
+    B, D, H, W = dims
+    out = _empty((B, *pdims, x.shape[-1]), x)
+    N.call("mic_crop_residual_bwd", N.ptr(x), None, N.ptr(out), B, D, H, W, *pdims, x.shape[-1])
+    return out
+
+
+def crop_add(res: Tensor, branch_p: Tensor, rowscale: Optional[Tensor], dims, pdims) -> Tensor:
+    B, D, H, W = dims
+    y = torch.empty_like(res)
+    N.call("mic_crop_residual", N.ptr(res), N.ptr(branch_p), N.ptr(rowscale), N.ptr(y), B, D, H, W, *pdims, res.shape[-1])
+    return y
+
+
+def crop_bwd(dy: Tensor, rowscale: Optional[Tensor], dims, pdims) -> Tensor:
+    B, D, H, W = dims
+    out = _empty((B, *pdims, dy.shape[-1]), dy)
+    N.call("mic_crop_residual_bwd", N.ptr(dy), N.ptr(rowscale), N.ptr(out), B, D, H, W, *pdims, dy.shape[-1])
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# shared pieces of the two transformer blocks
+# ----------------------------------------------------------------------------------------------------------
+def _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded):
+    B, D, H, W = dims
+    C = x.shape[-1]
+    T = B * D * H * W
+    if not padded:
+        return linear_fwd(o_p, C, pw, pb, T, C, C, res=x, rowscale=s1, rps=D * H * W).view(x.shape)
+    P = B * pdims[0] * pdims[1] * pdims[2]
+    pr = linear_fwd(o_p, C, pw, pb, P, C, C)
+    return crop_add(x, pr, s1, dims, pdims)
+
+
+def _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded):
+    """-> do_p (P,C), dpw, dpb"""
+    B, D, H, W = dims
+    C = dx1.shape[-1]
+    if not padded:
+        T = B * D * H * W
+        do_p = linear_bwd_data(dx1, C, pw, T, C, C, rowscale=s1, rps=D * H * W)
+        dpw, dpb = linear_bwd_weight(dx1, C, o_p, C, T, C, C, rowscale=s1, rps=D * H * W)
+        return do_p, dpw, dpb
+    P = B * pdims[0] * pdims[1] * pdims[2]
+    dpr = crop_bwd(dx1, s1, dims, pdims)
+    do_p = linear_bwd_data(dpr, C, pw, P, C, C)
+    dpw, dpb = linear_bwd_weight(dpr, C, o_p, C, P, C, C)
+    return do_p, dpw, dpb
+
+
+def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims):
+    B, D, H, W = dims
+    C = x1.shape[-1]
+    T = B * D * H * W
+    Hd = f1w.shape[0]
+    xn2, mean2, rstd2 = ln_fwd(x1, None, n2w, n2b, dims)
+    hpre = _empty((T, Hd), x1)
+    h = linear_fwd(xn2, C, f1w, f1b, T, Hd, C, act=True, pre=hpre)
+    y = linear_fwd(h, Hd, f2w, f2b, T, C, Hd, res=x1, rowscale=s2, rps=D * H * W).view(x1.shape)
+    return y, (xn2, mean2, rstd2, hpre, h)
+
+
+def _mlp_bwd(dy, x1, saved, n2w, f1w, f2w, s2, dims):
+    """-> dx1 (= dy + grad through LN/MLP), dn2w, dn2b, df1w, df1b, df2w, df2b"""
+    xn2, mean2, rstd2, hpre, h = saved
+    B, D, H, W = dims
+    C = x1.shape[-1]
+    T = B * D * H * W
+    Hd = f1w.shape[0]
+    rps = D * H * W
+    dh = linear_bwd_data(dy, C, f2w, T, C, Hd, gelu_pre=hpre, rowscale=s2, rps=rps)
+    df2w, df2b = linear_bwd_weight(dy, C, h, Hd, T, C, Hd, rowscale=s2, rps=rps)
+    dxn2 = linear_bwd_data(dh, Hd, f1w, T, Hd, C)
+    df1w, df1b = linear_bwd_weight(dh, Hd, xn2, C, T, Hd, C)
+    dx1, _, dn2w, dn2b = ln_bwd(dxn2, x1, None, n2w, mean2, rstd2, dy, None, dims)
+    return dx1, dn2w, dn2b, df1w, df1b, df2w, df2b
+
+
+class SelfBlockFn(torch.autograd.Function):
+    """TransformerBlock3D.forward (reference M:473-524) as one tape node.
+
+    args: x, s1, s2 (per-sample DropPath scales or None), heads, window, then 14 parameters:
+    norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b}, norm2.{w,b}, fc1.{w,b}, fc2.{w,b}."""
+
+    @staticmethod
+    def forward(ctx, x, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b):
+        N.check_cuda_f32(x, n1w, qw, kvw, pw, f1w, f2w)
+        B, D, H, W, C = x.shape
+        dims = (B, D, H, W)
+        ws, pdims = window_geometry((D, H, W), window)
+        padded = pdims != (D, H, W)
+        P = B * pdims[0] * pdims[1] * pdims[2]
+        xn_p, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims, pdims)
+        qkv = _empty((P, 3 * C), x)
+        linear_fwd(xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
+        linear_fwd(xn_p, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
+        o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
+        x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
+        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims)
+        ctx.save_for_backward(x, xn_p, mean1, rstd1, qkv, o_p, lse, x1, *mlp_saved, n1w, qw, kvw, pw, n2w, f1w, f2w,
+                              *( [s1] if s1 is not None else []), *([s2] if s2 is not None else []))
+        ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dims, pdims, ws, padded, heads, has1, has2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        x, xn_p, mean1, rstd1, qkv, o_p, lse, x1 = sv[:8]
+        mlp_saved = sv[8:13]
+        n1w, qw, kvw, pw, n2w, f1w, f2w = sv[13:20]
+        rest = sv[20:]
+        s1 = rest.pop(0) if has1 else None
+        s2 = rest.pop(0) if has2 else None
+        B, D, H, W = dims
+        C = x.shape[-1]
+        P = B * pdims[0] * pdims[1] * pdims[2]
+        dy = dy.contiguous()
+        dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+        do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+        dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+        dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
+        linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
+        dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
+        dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
+        dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+        return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
+                df2b)
+
+
+class CrossBlockFn(torch.autograd.Function):
+    """CrossTransformerBlock3D.forward (reference M:339-426): LN(x) -> offset net on cat[LN(x), xa] -> deformable
+    trilinear resampling of xa -> windowed cross attention (q from LN(x), k/v from the resampled xa) -> proj +
+    residual -> LN -> MLP -> residual.
+
+    args: x, xa, s1, s2, heads, window, then 19 parameters: norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b},
+    conv_offset.0 weight permuted to (27, 2C, 16) and bias, conv_offset.1.norm.{w,b}, conv_offset.3 weight (3,16),
+    norm2.{w,b}, fc1.{w,b}, fc2.{w,b}."""
+
+    @staticmethod
+    def forward(ctx, x, xa, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cb, lnw, lnb, w3, n2w, n2b,
+                f1w, f1b, f2w, f2b):
+        N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
+        B, D, H, W, C = x.shape
+        dims = (B, D, H, W)
+        ws, pdims = window_geometry((D, H, W), window)
+        padded = pdims != (D, H, W)
+        Dp, Hp, Wp = pdims
+        P = B * Dp * Hp * Wp
+        HC = cw.shape[-1]
+        xn_p, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims, pdims)
+        xa_p = pad_grid(xa, dims, pdims) if padded else xa
+        h16 = _empty((P, HC), x)
+        N.call("mic_conv3_fwd", N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(cw), N.ptr(cb), N.ptr(h16), B, Dp, Hp, Wp, Dp, Hp, Wp,
+               HC, 0)
+        pos = _empty((P, 3), x)
+        N.call("mic_offset_head_fwd", N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(pos), B, Dp, Hp, Wp, HC, LN_EPS)
+        samp = _empty((P, C), x)
+        N.call("mic_deform_sample_fwd", N.ptr(xa_p), N.ptr(pos), N.ptr(samp), B, Dp, Hp, Wp, Dp, Hp, Wp, C)
+        qkv = _empty((P, 3 * C), x)
+        linear_fwd(xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
+        linear_fwd(samp, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
+        o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
+        x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
+        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims)
+        ctx.save_for_backward(x, xa_p, xn_p, mean1, rstd1, h16, pos, samp, qkv, o_p, lse, x1, *mlp_saved, n1w, qw, kvw,
+                              pw, cw, lnw, lnb, w3, n2w, f1w, f2w, *([s1] if s1 is not None else []),
+                              *([s2] if s2 is not None else []))
+        ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dims, pdims, ws, padded, heads, has1, has2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        x, xa_p, xn_p, mean1, rstd1, h16, pos, samp, qkv, o_p, lse, x1 = sv[:12]
+        mlp_saved = sv[12:17]
+        n1w, qw, kvw, pw, cw, lnw, lnb, w3, n2w, f1w, f2w = sv[17:28]
+        rest = sv[28:]
+        s1 = rest.pop(0) if has1 else None
+        s2 = rest.pop(0) if has2 else None
+        B, D, H, W = dims
+        Dp, Hp, Wp = pdims
+        C = x.shape[-1]
+        P = B * Dp * Hp * Wp
+        HC = cw.shape[-1]
+        dy = dy.contiguous()
+        dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+        do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+        dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+        dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
+        dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
+        dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
+        dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
+        dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
+        dpos = _empty((P, 3), x)
+        N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa_p), N.ptr(pos), N.ptr(dxa_p), N.ptr(dpos), B, Dp, Hp, Wp, Dp,
+               Hp, Wp, C)
+        dh16 = _empty((P, HC), x)
+        dlnw = _zeros((HC,), x); dlnb = _zeros((HC,), x); dw3 = _zeros((3, HC), x)
+        N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
+               N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
+        N.call("mic_conv3_bwd_data", N.ptr(dh16), N.ptr(cw), N.ptr(dxn_p), C, 1, N.ptr(dxa_p), C, 1, B, Dp, Hp, Wp, Dp, Hp,
+               Wp, HC, 0)
+        dcw = torch.zeros_like(cw); dcb = _zeros((HC,), x)
+        N.call("mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp, Hp, Wp,
+               Dp, Hp, Wp, HC, 0)
+        dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+        if padded:
+            dxa = dxa_p[:, :D, :H, :W, :].contiguous()
+        else:
+            dxa = dxa_p
+        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, dcb, dlnw, dlnb, dw3,
+                dn2w, dn2b, df1w, df1b, df2w, df2b)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# non-block operators
+# ----------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last axis of a token grid, optionally on the channel concatenation [x0 | x1]
+    (``norm`` M:1011-1012; cat + ``norm2`` M:1033-1034)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, w, b):
+        N.check_cuda_f32(x0, x1, w, b)
+        B = x0.shape[0]
+        rows = x0.numel() // x0.shape[-1] // B
+        dims = (B, 1, 1, rows)
+        y, mean, rstd = ln_fwd(x0, x1, w, b, dims)
+        ctx.save_for_backward(x0, x1 if x1 is not None else x0, w, mean, rstd)
+        ctx.meta = (dims, x1 is not None)
+        C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+        return y.view(*x0.shape[:-1], C)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x0, x1, w, mean, rstd = ctx.saved_tensors
+        dims, has1 = ctx.meta
+        dx0, dx1, dw, db = ln_bwd(dy.contiguous(), x0, x1 if has1 else None, w, mean, rstd, None, None, dims)
+        return dx0, dx1, dw, db
+
+
+class SkipLinearFn(torch.autograd.Function):
+    """concat_back_dim: Linear(2C -> C) on cat[up, skip] (reference M:1027-1030) as two accumulating GEMMs."""
+
+    @staticmethod
+    def forward(ctx, a, b, w, bias):
+        N.check_cuda_f32(a, b, w, bias)
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        Cout = w.shape[0]
+        T = a.numel() // Ca
+        y = linear_fwd(a, Ca, w, bias, T, Cout, Ca, ldw=Ca + Cb)
+        linear_fwd(b, Cb, w, None, T, Cout, Cb, ldw=Ca + Cb, w_col=Ca, out=y, ldy=Cout, accumulate=True)
+        ctx.save_for_backward(a, b, w)
+        return y.view(*a.shape[:-1], Cout)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        a, b, w = ctx.saved_tensors
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        Cout = w.shape[0]
+        T = a.numel() // Ca
+        dy = dy.contiguous()
+        da = linear_bwd_data(dy, Cout, w, T, Cout, Ca, ldw=Ca + Cb).view(a.shape)
+        db_ = linear_bwd_data(dy, Cout, w, T, Cout, Cb, ldw=Ca + Cb, w_col=Ca).view(b.shape)
+        dW = torch.zeros_like(w)
+        _, dbias = linear_bwd_weight(dy, Cout, a, Ca, T, Cout, Ca, dW=dW, lddw=Ca + Cb)
+        linear_bwd_weight(dy, Cout, b, Cb, T, Cout, Cb, dW=dW, lddw=Ca + Cb, dw_col=Ca, want_bias=False)
+        return da, db_, dW, dbias
+
+
+def block_permute(src: Tensor, dst: Tensor, B, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, src_off=0):
+    N.call("mic_block_permute", src.data_ptr() + 4 * src_off if to_rows else src.data_ptr(),
+           dst.data_ptr() if to_rows else dst.data_ptr() + 4 * src_off, B, Dq, Hq, Wq, k, C, grid_batch_stride, int(to_rows))
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """PatchEmbed3D (reference M:860-878, norm off): Conv3d(1->E,k4,s4) of channel ``ch`` of the (B,2,D,H,W) input,
+    emitted channels-last (M:1001-1002).  4^3 gather -> (rows, 64) -> GEMM.  No input gradient."""
+
+    @staticmethod
+    def forward(ctx, vol, ch, w, b):
+        N.check_cuda_f32(vol, w, b)
+        B, Cin, D, H, W = vol.shape
+        if D % 4 or H % 4 or W % 4:
+            raise RuntimeError("PatchEmbed3D: sizes not divisible by 4 need the pad branch (SURVEY 8f rank 4): unsupported")
+        Dq, Hq, Wq = D // 4, H // 4, W // 4
+        E = w.shape[0]
+        rows = _empty((B * Dq * Hq * Wq, 64), vol)
+        block_permute(vol, rows, B, Dq, Hq, Wq, 4, 1, Cin * D * H * W, True, src_off=ch * D * H * W)
+        y = linear_fwd(rows, 64, w, b, rows.shape[0], E, 64)
+        ctx.save_for_backward(rows)
+        ctx.E = E
+        ctx.wshape = tuple(w.shape)
+        return y.view(B, Dq, Hq, Wq, E)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (rows,) = ctx.saved_tensors
+        E = ctx.E
+        dy = dy.contiguous()
+        dW, db = linear_bwd_weight(dy, E, rows, 64, rows.shape[0], E, 64)
+        return None, None, dW.view(ctx.wshape), db
+
+
+class PatchMergeFn(torch.autograd.Function):
+    """PatchMerging (reference M:542-561): Conv3d(C->2C,k2,s2) + LayerNorm(2C).  w2 is the conv weight permuted
+    to (2C, kz,ky,kx, C) and flattened to (2C, 8C)."""
+
+    @staticmethod
+    def forward(ctx, x, w2, b, nw, nb):
+        N.check_cuda_f32(x, w2, b, nw, nb)
+        B, D, H, W, C = x.shape
+        if D % 2 or H % 2 or W % 2:
+            raise RuntimeError("PatchMerging: odd sizes need the pad branch (SURVEY 8f rank 4): unsupported")
+        Dq, Hq, Wq = D // 2, H // 2, W // 2
+        R = B * Dq * Hq * Wq
+        Co = w2.shape[0]
+        rows = _empty((R, 8 * C), x)
+        block_permute(x, rows, B, Dq, Hq, Wq, 2, C, D * H * W * C, True)
+        z = linear_fwd(rows, 8 * C, w2, b, R, Co, 8 * C)
+        y, mean, rstd = ln_fwd(z, None, nw, nb, (B, Dq, Hq, Wq))
+        ctx.save_for_backward(rows, z, mean, rstd, w2, nw)
+        ctx.meta = (B, Dq, Hq, Wq, C, Co)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        rows, z, mean, rstd, w2, nw = ctx.saved_tensors
+        B, Dq, Hq, Wq, C, Co = ctx.meta
+        R = B * Dq * Hq * Wq
+        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, Dq, Hq, Wq))
+        drows = linear_bwd_data(dz, Co, w2, R, Co, 8 * C)
+        dW, db = linear_bwd_weight(dz, Co, rows, 8 * C, R, Co, 8 * C)
+        dx = _empty((B, 2 * Dq, 2 * Hq, 2 * Wq, C), dz)
+        block_permute(drows, dx, B, Dq, Hq, Wq, 2, C, 8 * Dq * Hq * Wq * C, False)
+        return dx, dW, db, dnw, dnb
+
+
+class PatchExpandFn(torch.autograd.Function):
+    """PatchExpand (reference M:571-579): ConvTranspose3d(C->C/2,k2,s2) + LayerNorm(C/2).  wk is the weight permuted
+    to (C, kz,ky,kx, C/2) and flattened to (C, 8*C/2); b8 is the bias tiled 8x (one per sub-voxel)."""
+
+    @staticmethod
+    def forward(ctx, x, wk, b8, nw, nb):
+        N.check_cuda_f32(x, wk, b8, nw, nb)
+        B, D, H, W, C = x.shape
+        Co = nw.shape[0]
+        T = B * D * H * W
+        rows = linear_fwd(x, C, wk, b8, T, 8 * Co, C, w_is_kn=True)
+        z = _empty((B, 2 * D, 2 * H, 2 * W, Co), x)
+        block_permute(rows, z, B, D, H, W, 2, Co, 8 * D * H * W * Co, False)
+        y, mean, rstd = ln_fwd(z, None, nw, nb, (B, 2 * D, 2 * H, 2 * W))
+        ctx.save_for_backward(x, z, mean, rstd, wk, nw)
+        ctx.meta = (B, D, H, W, C, Co)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, z, mean, rstd, wk, nw = ctx.saved_tensors
+        B, D, H, W, C, Co = ctx.meta
+        T = B * D * H * W
+        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, 2 * D, 2 * H, 2 * W))
+        drows = _empty((T, 8 * Co), dz)
+        block_permute(dz, drows, B, D, H, W, 2, Co, 8 * D * H * W * Co, True)
+        dx = linear_bwd_data(drows, 8 * Co, wk, T, 8 * Co, C, w_is_kn=True).view(x.shape)
+        dW, db8 = linear_bwd_weight(drows, 8 * Co, x, C, T, 8 * Co, C, w_is_kn=True)
+        return dx, dW, db8, dnw, dnb
+
+
+class SegHeadFn(torch.autograd.Function):
+    """Decoder tail (reference M:1033-1037 + Head M:1053): cat[moving, fixed] -> norm2 -> ConvTranspose3d(2E->E/2,k4,s4)
+    -> Conv3d(E/2->num_classes,k3,p1), NCDHW logits.  wr: (2E, 64*E/2) permuted (kz,ky,kx,co); br64: bias tiled 64x;
+    wo: out_conv weight permuted to (27, E/2, NC)."""
+
+    @staticmethod
+    def forward(ctx, xm, xf, n2w, n2b, wr, br64, wo, bo):
+        N.check_cuda_f32(xm, xf, n2w, n2b, wr, br64, wo, bo)
+        B, D, H, W, E = xm.shape
+        T = B * D * H * W
+        Ch = wo.shape[1]
+        NC = wo.shape[2]
+        xn, mean, rstd = ln_fwd(xm, xf, n2w, n2b, (B, D, H, W))
+        rows = linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True)
+        y24 = _empty((B, 4 * D, 4 * H, 4 * W, Ch), xm)
+        block_permute(rows, y24, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
+        del rows
+        logits = _empty((B, NC, 4 * D, 4 * H, 4 * W), xm)
+        N.call("mic_conv3_fwd", N.ptr(y24), Ch, None, 0, N.ptr(wo), N.ptr(bo), N.ptr(logits), B, 4 * D, 4 * H, 4 * W, 4 * D,
+               4 * H, 4 * W, NC, 1)
+        ctx.save_for_backward(xm, xf, n2w, mean, rstd, xn, wr, y24, wo)
+        ctx.meta = (B, D, H, W, E, Ch, NC)
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlog):
+        xm, xf, n2w, mean, rstd, xn, wr, y24, wo = ctx.saved_tensors
+        B, D, H, W, E, Ch, NC = ctx.meta
+        T = B * D * H * W
+        dlog = dlog.contiguous()
+        dy24 = torch.empty_like(y24)
+        N.call("mic_conv3_bwd_data", N.ptr(dlog), N.ptr(wo), N.ptr(dy24), Ch, 0, None, 0, 0, B, 4 * D, 4 * H, 4 * W, 4 * D,
+               4 * H, 4 * W, NC, 1)
+        dwo = torch.zeros_like(wo); dbo = _zeros((NC,), xm)
+        N.call("mic_conv3_bwd_weight", N.ptr(dlog), N.ptr(y24), Ch, None, 0, N.ptr(dwo), N.ptr(dbo), B, 4 * D, 4 * H, 4 * W,
+               4 * D, 4 * H, 4 * W, NC, 1)
+        drows = _empty((T, 64 * Ch), xm)
+        block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
+        del dy24
+        dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
+        dwr, dbr64 = linear_bwd_weight(drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
+        dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W))
+        return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, dbo
+
+
+class DiceBceLossFn(torch.autograd.Function):
+    """MDiceLoss.forward (reference loss/dice.py:158-166) in one reduction pass + closed-form backward.
+    ``group`` (a torch.distributed process group or None): all-reduce the 4*C partial sums so that the Dice
+    terms span the GLOBAL batch; None keeps the reference's per-process semantics."""
+
+    @staticmethod
+    def forward(ctx, logits, target, group, world):
+        N.check_cuda_f32(logits, target)
+        if logits.shape != target.shape:
+            raise RuntimeError(f"MDiceLoss: logits {tuple(logits.shape)} vs target {tuple(target.shape)}")
+        B, C = logits.shape[:2]
+        S = logits[0, 0].numel()
+        sums = torch.zeros(C * 4, device=logits.device, dtype=torch.float64)
+        N.call("mic_dice_bce_partial", N.ptr(logits), N.ptr(target), N.ptr(sums), B, C, S)
+        n = float(B * S)
+        if group is not None and world > 1:
+            torch.distributed.all_reduce(sums, group=group)
+            n *= world
+        loss = _empty((), logits)
+        coef = _empty((C * 3,), logits)
+        N.call("mic_dice_bce_finalize", N.ptr(sums), N.ptr(loss), N.ptr(coef), C, n)
+        ctx.save_for_backward(logits, target, coef)
+        ctx.n = n
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        logits, target, coef = ctx.saved_tensors
+        B, C = logits.shape[:2]
+        S = logits[0, 0].numel()
+        dl = torch.empty_like(logits)
+        dloss = dloss.contiguous().float()
+        N.call("mic_dice_bce_bwd", N.ptr(logits), N.ptr(target), N.ptr(coef), N.ptr(dloss), N.ptr(dl), B, C, S, ctx.n)
+        return dl, None, None, None
+
+
+class DeformSampleFn(torch.autograd.Function):
+    """SpatialTransformer.forward (reference models/STN.py:9-32) on channels-last tensors:
+    src (B,D,H,W,C), pos (B,D,H,W,3) -> (B,D,H,W,C)."""
+
+    @staticmethod
+    def forward(ctx, src, pos):
+        N.check_cuda_f32(src, pos)
+        B, D, H, W, C = src.shape
+        out = torch.empty_like(src)
+        N.call("mic_deform_sample_fwd", N.ptr(src), N.ptr(pos), N.ptr(out), B, D, H, W, D, H, W, C)
+        ctx.save_for_backward(src, pos)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        src, pos = ctx.saved_tensors
+        B, D, H, W, C = src.shape
+        dsrc = torch.zeros_like(src)
+        dpos = torch.empty_like(pos)
+        N.call("mic_deform_sample_bwd", N.ptr(dout.contiguous()), N.ptr(src), N.ptr(pos), N.ptr(dsrc), N.ptr(dpos), B, D, H,
+               W, D, H, W, C)
+        return dsrc, dpos
