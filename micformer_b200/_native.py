@@ -81,10 +81,95 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_prof = None   # name -> [events..., flops, bytes, count] when profiling is on (bench.py's per-kernel pass)
+
+
+def _prod(*v):
+    r = 1
+    for x in v:
+        r *= x
+    return r
+
+
+# algorithmic (flops, bytes) per call from the C-ABI arguments (stream excluded); DESIGN.md states the formulas
+def _cost_conv3(B, D, H, W, Dp, Hp, Wp, Cin, Co):
+    P = B * Dp * Hp * Wp
+    return 2 * 27 * Cin * Co * P, 4 * (B * D * H * W * Cin + P * Co + 27 * Cin * Co)
+
+
+COST = {
+    "mic_linear_fwd": lambda a: (2 * a[8] * a[9] * a[10], 4 * (a[8] * a[10] + a[9] * a[10] + a[8] * a[9] *
+                                                                (1 + (a[12] is not None) + (a[14] is not None)))),
+    "mic_linear_bwd_data": lambda a: (2 * a[7] * a[8] * a[9], 4 * (a[7] * a[8] + a[8] * a[9] + a[7] * a[9] *
+                                                                   (1 + (a[10] is not None)))),
+    "mic_linear_bwd_weight": lambda a: (2 * a[8] * a[9] * a[10], 4 * (a[8] * a[9] + a[8] * a[10] + a[9] * a[10])),
+    "mic_conv3_fwd": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[1] + a[3], a[14]),
+    "mic_conv3_bwd_data": lambda a: _cost_conv3(a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[3] + a[6], a[15]),
+    "mic_conv3_bwd_weight": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[2] + a[4], a[14]),
+    "mic_window_attn_fwd": lambda a: (4 * _prod(*a[8:12]) * a[12] * a[13] * _prod(*a[14:17]),
+                                      4 * (4 * _prod(*a[8:12]) * a[12] * a[13] + _prod(*a[8:12]) * a[12])),
+    "mic_window_attn_bwd": lambda a: (10 * _prod(*a[14:18]) * a[18] * a[19] * _prod(*a[20:23]),
+                                      4 * (8 * _prod(*a[14:18]) * a[18] * a[19] + _prod(*a[14:18]) * a[18])),
+    "mic_layernorm_fwd": lambda a: (0, 4 * (a[1] + a[3]) * (_prod(*a[9:13]) + a[9] * _prod(*a[13:16]))),
+    "mic_layernorm_bwd": lambda a: (0, 4 * (a[2] + a[4]) * (2 * _prod(*a[14:18]) + a[14] * _prod(*a[18:21]) +
+                                                          (a[8] is not None) * _prod(*a[14:18]))),
+    "mic_deform_sample_fwd": lambda a: (0, 4 * (a[3] * _prod(*a[4:7]) * a[10] + a[3] * _prod(*a[7:10]) * (a[10] + 3))),
+    "mic_deform_sample_bwd": lambda a: (0, 4 * (2 * a[5] * _prod(*a[6:9]) * a[12] + a[5] * _prod(*a[9:12]) * (a[12] + 6))),
+    "mic_block_permute": lambda a: (0, 8 * a[2] * a[3] * a[4] * a[5] * a[6] ** 3 * a[7]),
+    "mic_dice_bce_partial": lambda a: (0, 8 * a[3] * a[4] * a[5]),
+    "mic_dice_bce_bwd": lambda a: (0, 12 * a[5] * a[6] * a[7]),
+    "mic_offset_head_fwd": lambda a: (0, 4 * _prod(*a[5:9]) * (a[9] + 3)),
+    "mic_offset_head_bwd": lambda a: (0, 4 * _prod(*a[9:13]) * (2 * a[13] + 3)),
+    "mic_crop_residual": lambda a: (0, 12 * _prod(*a[4:8]) * a[11]),
+    "mic_crop_residual_bwd": lambda a: (0, 4 * a[3] * (_prod(*a[4:7]) + _prod(*a[7:10])) * a[10]),
+}
+
+
+TAG = {
+    "mic_linear_fwd": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",
+    "mic_linear_bwd_data": lambda a: f"M{a[7]}xN{a[8]}xK{a[9]}",
+    "mic_linear_bwd_weight": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",
+    "mic_conv3_fwd": lambda a: f"Cin{a[1] + a[3]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
+    "mic_conv3_bwd_data": lambda a: f"Cin{a[3] + a[6]}xCo{a[15]}@{a[8] * a[12] * a[13] * a[14]}",
+    "mic_conv3_bwd_weight": lambda a: f"Cin{a[2] + a[4]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
+}
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = {}
+
+
+def profile_end() -> dict:
+    """-> {name: {"ms": total device ms, "calls": n, "flops": algorithmic flops, "bytes": algorithmic bytes}}"""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for name, rec in (_prof or {}).items():
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in rec["ev"])
+        out[name] = {"ms": ms, "calls": len(rec["ev"]), "flops": rec["flops"], "bytes": rec["bytes"]}
+    _prof = None
+    return out
+
+
 def call(name: str, *args):
     """Invoke an ``int``-returning entry point on the current CUDA stream; raise on a non-zero code."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    if _prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        tg = TAG.get(name)
+        key = f"{name}[{tg(args)}]" if tg is not None else name
+        rec = _prof.setdefault(key, {"ev": [], "flops": 0, "bytes": 0})
+        rec["ev"].append((e0, e1))
+        fn = COST.get(name)
+        if fn is not None:
+            f, b = fn(args)
+            rec["flops"] += f; rec["bytes"] += b
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
 

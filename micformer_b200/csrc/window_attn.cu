@@ -27,7 +27,7 @@ __device__ __forceinline__ int64_t token_row(const WinGeom& g, int64_t win, int 
 }
 
 template <int HD>
-__global__ void __launch_bounds__(384) window_attn_fwd_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+__global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_fwd_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                        const float* __restrict__ v, int ldkv, float* __restrict__ out, int ldo,
                                        float* __restrict__ lse, WinGeom g, float scale) {
     extern __shared__ __align__(16) float smem[];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(384) window_attn_fwd_kernel(const float* __res
 // Backward: pass A (thread = query) computes dq; pass B (thread = key) computes dk, dv.  Scores are recomputed
 // from q, k and the saved log-sum-exp.
 template <int HD>
-__global__ void __launch_bounds__(384) window_attn_bwd_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+__global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_bwd_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                        const float* __restrict__ v, int ldkv, const float* __restrict__ out,
                                        const float* __restrict__ dout, int ldo, const float* __restrict__ lse,
                                        float* __restrict__ dq, int lddq, float* __restrict__ dk,
@@ -284,8 +284,13 @@ int simt_window_attn_fwd(const float* q, int ldq, const float* k, const float* v
         case 16: return launch_fwd<16>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st);
         case 24: return launch_fwd<24>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st);
         case 32: return launch_fwd<32>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st);
-        default: return fail(MIC_ERR_UNSUPPORTED, "window_attn: head_dim %d not in {8,12,16,24,32}", hd);
+        case 48: if (g.N <= 128) return launch_fwd<48>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st); break;
+        case 64: if (g.N <= 128) return launch_fwd<64>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st); break;
+        case 96: if (g.N <= 128) return launch_fwd<96>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale, st); break;
+        default: break;
     }
+    return fail(MIC_ERR_UNSUPPORTED, "window_attn: head_dim %d (window %d tokens) not built: {8,12,16,24,32} any window, "
+                "{48,64,96} windows <= 128 tokens", hd, g.N);
 }
 
 int simt_window_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* out,
@@ -304,9 +309,14 @@ int simt_window_attn_bwd(const float* q, int ldq, const float* k, const float* v
         case 16: return BWD(16);
         case 24: return BWD(24);
         case 32: return BWD(32);
-        default: return fail(MIC_ERR_UNSUPPORTED, "window_attn: head_dim %d not in {8,12,16,24,32}", hd);
+        case 48: if (g.N <= 128) return BWD(48); break;
+        case 64: if (g.N <= 128) return BWD(64); break;
+        case 96: if (g.N <= 128) return BWD(96); break;
+        default: break;
     }
 #undef BWD
+    return fail(MIC_ERR_UNSUPPORTED, "window_attn: head_dim %d (window %d tokens) not built: {8,12,16,24,32} any window, "
+                "{48,64,96} windows <= 128 tokens", hd, g.N);
 }
 
 }  // namespace mic

@@ -1,0 +1,74 @@
+"""Data parallelism over volumes: one process per GPU, parameters replicated, ONE gradient all-reduce (mean) per
+step over NCCL (NVLink 5 / NVSwitch) -- the path has no other exchange.  The reference itself is
+single-GPU (train_mmwhs_noPad.py:413); this is what BASELINE.json's 1/2/4/8-GPU rows add.
+
+``GradSync`` packs gradients into flat buckets (reverse registration order ~ the order backward produces them),
+all-reduces each bucket asynchronously and scatters the averages back.  Parameters that never receive a gradient
+(``swin.concat_back_dim.0.*`` is unused by the forward, reference M:1015-1016 / SURVEY F12) are skipped -- the
+set must be identical on every rank, which is checked once.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.bucket_bytes = bucket_bytes
+        self.group = process_group
+        self._plan = None      # list of lists of param indices
+        self._flat = None
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _build_plan(self):
+        live = [i for i, p in enumerate(self.params) if p.grad is not None]
+        if dist.is_initialized() and self.world > 1:
+            # every rank must skip the same parameters
+            sig = torch.tensor([len(live), sum(live) % 1000003], dtype=torch.int64, device=self.params[0].device)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("GradSync: ranks disagree on which parameters received gradients")
+        plan, cur, size = [], [], 0
+        for i in reversed(live):
+            n = self.params[i].numel() * self.params[i].element_size()
+            if cur and size + n > self.bucket_bytes:
+                plan.append(cur); cur, size = [], 0
+            cur.append(i); size += n
+        if cur:
+            plan.append(cur)
+        self._plan = plan
+        p0 = self.params[0]
+        self._flat = [torch.empty(sum(self.params[i].numel() for i in b), device=p0.device, dtype=p0.dtype) for b in plan]
+
+    def sync(self) -> None:
+        """Average ``.grad`` across ranks in place.  Call after ``backward()``."""
+        if self.world <= 1:
+            return
+        if self._plan is None:
+            self._build_plan()
+        works = []
+        inv = 1.0 / self.world
+        for flat, idxs in zip(self._flat, self._plan):
+            grads = [self.params[i].grad for i in idxs]
+            views = list(torch.split(flat, [g.numel() for g in grads]))
+            torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+            flat.mul_(inv)
+            works.append(dist.all_reduce(flat, group=self.group, async_op=True))
+        for w, flat, idxs in zip(works, self._flat, self._plan):
+            w.wait()
+            grads = [self.params[i].grad for i in idxs]
+            views = list(torch.split(flat, [g.numel() for g in grads]))
+            torch._foreach_copy_([g.reshape(-1) if g.is_contiguous() else g for g in grads], views)
+
+    def skipped(self) -> List[int]:
+        live = set(i for b in (self._plan or []) for i in b)
+        return [i for i in range(len(self.params)) if i not in live]

@@ -365,12 +365,16 @@ def test_full_size_vs_oracle(cfgname, S):
     mism = (yc.argmax(1) != logits.argmax(1)) & (margin > 2 * err)
     assert int(mism.sum()) == 0
     assert abs(float(loss) - float(loss_ref)) < 1e-5
+    # per-tensor relative error with an absolute floor tied to the global gradient norm: some tensors have
+    # mathematically zero gradients (e.g. q of a window whose sampled keys are all identical) and hold only noise
+    gl2 = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values() if g is not None)))
     worst = 0.0
     for k, p in head.named_parameters():
         if grads[k] is None:
             assert p.grad is None
             continue
-        worst = max(worst, rel_err(p.grad.cpu(), grads[k]))
+        d = float((p.grad.cpu().double() - grads[k].double()).norm())
+        worst = max(worst, d / (float(grads[k].double().norm()) + 1e-6 * gl2))
     assert worst < 2e-3, worst
 
 
