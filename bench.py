@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MICFORMER_GEMM_MODE", "0")))
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel table (JSON) here")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("MICFORMER_CUDA_GRAPH", "0")))
     return ap.parse_args()
 
@@ -209,6 +212,13 @@ def run_ours(args):
 
     for _ in range(max(3, args.warmup)):
         step(x_d, lab_d)
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(x_d, lab_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # --- device-resident throughput ---------------------------------------------------------------------
     clocks = ClockSampler(local)
     clocks.start()
@@ -247,6 +257,15 @@ def run_ours(args):
                    "calls_per_step": v["calls"] // ksteps,
                    "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] > 0 else None,
                    "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["ms"] > 0 else None} for k, v in top[:12]]
+        if args.dump_kernels:
+            os.makedirs(os.path.dirname(os.path.abspath(args.dump_kernels)), exist_ok=True)
+            with open(args.dump_kernels, "w") as f:
+                json.dump({"steps": ksteps, "total_ms_per_step": tot / ksteps,
+                           "kernels": [{"kernel": k, "ms_per_step": v["ms"] / ksteps, "calls_per_step": v["calls"] / ksteps,
+                                        "us_per_call": 1e3 * v["ms"] / v["calls"], "share": v["ms"] / tot,
+                                        "gbs": v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else None,
+                                        "tflops": v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else None}
+                                       for k, v in top]}, f, indent=1)
         name, v = top[0]
         ach = v["bytes"] / (v["ms"] * 1e6)        # GB/s: algorithmic bytes / event-timed duration
         roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],

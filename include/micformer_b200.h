@@ -34,8 +34,8 @@ const char* mic_last_error_string(void);
 /* number of kernel launches issued by this library in the calling process since load / last reset */
 int64_t mic_launch_count(void);
 void mic_reset_launch_count(void);
-/* 0 = fp32 CUDA-core GEMMs (exact parity path), 1 = tcgen05 TF32 tensor-core GEMMs where shapes allow,
- * 2 = tcgen05 3xTF32 split (fp32-faithful) */
+/* 0 = fp32 CUDA-core GEMMs (exact parity path), 1 = tcgen05 TF32 tensor-core GEMMs where shapes allow
+ * (fp32 in/out, operands read as tf32, fp32 accumulate in TMEM), 2 = reserved (3xTF32 split; currently == 0) */
 int mic_set_gemm_mode(int mode);
 int mic_get_gemm_mode(void);
 

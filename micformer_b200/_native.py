@@ -64,6 +64,10 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
     _lib = lib
+    mode = os.environ.get("MICFORMER_GEMM_MODE")
+    if mode is not None:
+        if lib.mic_set_gemm_mode(int(mode)) != 0:
+            raise RuntimeError(f"MICFORMER_GEMM_MODE={mode}: " + lib.mic_last_error_string().decode())
     return lib
 
 

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see messages above")
-    link = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+    link = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

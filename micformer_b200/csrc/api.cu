@@ -28,6 +28,10 @@ int simt_linear_bwd_weight(const float*, int, const float*, int, float*, int, in
 // gemm_tc.cu (tcgen05); return MIC_ERR_UNSUPPORTED when the shape is not taken
 int tc_linear_fwd(const float*, int, const float*, int, int, const float*, float*, int, int, int, int, int, float*, int,
                   const float*, int, const float*, int, int, int, cudaStream_t);
+int tc_linear_bwd_data(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, int,
+                       const float*, int, int, int, cudaStream_t);
+int tc_linear_bwd_weight(const float*, int, const float*, int, float*, int, int, float*, int, int, int, const float*, int, int,
+                         cudaStream_t);
 // window_attn.cu
 int simt_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int,
                          int, int, int, int, float, cudaStream_t);
@@ -56,7 +60,7 @@ extern "C" int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
     MIC_REQUIRE(X && W && Y && M > 0 && N > 0 && K > 0, "linear_fwd: bad arguments (M=%d N=%d K=%d)", M, N, K);
     MIC_REQUIRE(!(accumulate && (act || res)), "linear_fwd: accumulate cannot be combined with act/res");
     const int mode = g_gemm_mode.load();
-    if (mode > 0) {
+    if (mode == 1) {
         int rc = tc_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
                                rows_per_sample, accumulate, mode, (cudaStream_t)stream);
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
@@ -69,6 +73,12 @@ extern "C" int mic_linear_bwd_data(const float* dY, int lddy, const float* W, in
                                    int M, int N, int K, const float* gelu_pre, int ldpre, const float* rowscale,
                                    int rows_per_sample, int accumulate, void* stream) {
     MIC_REQUIRE(dY && W && dX && M > 0 && N > 0 && K > 0, "linear_bwd_data: bad arguments");
+    const int mode = g_gemm_mode.load();
+    if (mode == 1) {
+        int rc = tc_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
+                                    accumulate, mode, (cudaStream_t)stream);
+        if (rc != MIC_ERR_UNSUPPORTED) return rc;
+    }
     return simt_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
                                 accumulate, (cudaStream_t)stream);
 }
@@ -77,6 +87,12 @@ extern "C" int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, 
                                      float* db, int M, int N, int K, const float* rowscale, int rows_per_sample,
                                      void* stream) {
     MIC_REQUIRE(dY && X && dW && M > 0 && N > 0 && K > 0, "linear_bwd_weight: bad arguments");
+    const int mode = g_gemm_mode.load();
+    if (mode == 1) {
+        int rc = tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample, mode,
+                                      (cudaStream_t)stream);
+        if (rc != MIC_ERR_UNSUPPORTED) return rc;
+    }
     return simt_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample,
                                   (cudaStream_t)stream);
 }

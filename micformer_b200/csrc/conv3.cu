@@ -26,7 +26,8 @@ __device__ __forceinline__ float4 ld_cat4(const float* __restrict__ x0, int C0, 
 template <int COP>
 __global__ void __launch_bounds__(128) conv3_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                                         const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                        float* __restrict__ y, ConvGeom g, int out_ncdhw) {
+                                                        float* __restrict__ y, ConvGeom g, int out_ncdhw,
+                                                        int units_per_split) {
     constexpr int OG = COP / 4;          // output groups of 4
     constexpr int PG = 128 / OG;         // position groups
     constexpr int TP = PG * 4;           // positions per CTA
@@ -58,9 +59,16 @@ __global__ void __launch_bounds__(128) conv3_fwd_kernel(const float* __restrict_
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 
-    for (int tap = 0; tap < 27; ++tap) {
+    // K is split over blockIdx.y in units of (tap, 32-channel chunk); partial sums are atomically accumulated
+    const int nchunks = (Cin + KC - 1) / KC;
+    const int unit_begin = blockIdx.y * units_per_split;
+    const int unit_end = min(27 * nchunks, unit_begin + units_per_split);
+    const bool split = gridDim.y > 1;
+    for (int unit = unit_begin; unit < unit_end; ++unit) {
+        const int tap = unit / nchunks;
         const int tz = tap / 9 - 1, ty = (tap / 3) % 3 - 1, tx = tap % 3 - 1;
-        for (int c0 = 0; c0 < Cin; c0 += KC) {
+        {
+            const int c0 = (unit % nchunks) * KC;
             // gather A: TP positions x 8 float4
             for (int idx = tid; idx < TP * 8; idx += 128) {
                 const int pos = idx >> 3, c4 = (idx & 7) * 4;
@@ -103,13 +111,15 @@ __global__ void __launch_bounds__(128) conv3_fwd_kernel(const float* __restrict_
         for (int j = 0; j < 4; ++j) {
             const int o = og * 4 + j;
             if (o >= g.Co) continue;
-            const float v = acc[i][j] + (bias ? bias[o] : 0.f);
+            const float v = acc[i][j] + ((bias && blockIdx.y == 0) ? bias[o] : 0.f);
+            float* dst;
             if (out_ncdhw) {
                 const int64_t b = p / S;
-                y[(b * g.Co + o) * S + (p - b * S)] = v;
+                dst = y + (b * g.Co + o) * S + (p - b * S);
             } else {
-                y[p * g.Co + o] = v;
+                dst = y + p * g.Co + o;
             }
+            if (split) atomicAdd(dst, v); else *dst = v;
         }
     }
 }
@@ -326,8 +336,21 @@ extern "C" int mic_conv3_fwd(const float* x0, int C0, const float* x1, int C1, c
     ConvGeom g{B, D, H, W, Dp, Hp, Wp, C0, C1, Co};
     const int64_t P = (int64_t)B * Dp * Hp * Wp;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Co <= 8) conv3_fwd_kernel<8><<<(unsigned)ceil_div64(P, 256), 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw);
-    else conv3_fwd_kernel<16><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw);
+    const int TP = Co <= 8 ? 256 : 128;
+    const int64_t tiles = ceil_div64(P, TP);
+    const int units = 27 * ceil_div(C0 + C1, 32);
+    int splits = (int)ceil_div64((int64_t)num_sms() * 3, tiles);
+    if (splits > units / 2) splits = units / 2;
+    if (splits < 1) splits = 1;
+    const int ups = ceil_div(units, splits);
+    splits = ceil_div(units, ups);
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(y, 0, (size_t)P * Co * sizeof(float), st);
+        if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "conv3_fwd memset: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)tiles, splits);
+    if (Co <= 8) conv3_fwd_kernel<8><<<grid, 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw, ups);
+    else conv3_fwd_kernel<16><<<grid, 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw, ups);
     return check_launch("conv3_fwd_kernel");
 }
 

@@ -167,17 +167,17 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs p) {
 }
 
 // db[j] += sum_m rowscale[m]*dY[m,j]
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N,
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N,
                                                      const float* __restrict__ rowscale, int rps,
                                                      float* __restrict__ out, int rows_per_block) {
-    // block (32 x 8): x -> column, y -> row lane
-    __shared__ float red[8][33];
+    // block (32 x 32): x -> column, y -> row lane
+    __shared__ float red[32][33];
     const int j = blockIdx.x * 32 + threadIdx.x;
     const int m0 = blockIdx.y * rows_per_block;
     const int m1 = min(M, m0 + rows_per_block);
     float s = 0.f;
     if (j < N)
-        for (int m = m0 + threadIdx.y; m < m1; m += 8) {
+        for (int m = m0 + threadIdx.y; m < m1; m += 32) {
             float v = X[(int64_t)m * ldx + j];
             if (rowscale) v *= rowscale[m / rps];
             s += v;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     if (threadIdx.y == 0 && j < N) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
         atomicAdd(&out[j], t);
     }
 }
@@ -202,9 +202,9 @@ int launch_gemm(const GemmArgs& p, bool a_rc, bool b_rc, int splits, cudaStream_
 }
 
 int colsum(const float* X, int64_t ldx, int M, int N, const float* rowscale, int rps, float* out, cudaStream_t st) {
-    int rows_per_block = 512;
+    int rows_per_block = M >= 16384 ? 512 : 128;
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
-    colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, ldx, M, N, rowscale, rps, out, rows_per_block);
+    colsum_kernel<<<grid, dim3(32, 32), 0, st>>>(X, ldx, M, N, rowscale, rps, out, rows_per_block);
     return check_launch("colsum_kernel");
 }
 

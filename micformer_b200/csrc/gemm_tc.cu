@@ -1,9 +1,506 @@
-// tcgen05 tensor-core GEMM path (placeholder until the TMA/UMMA kernel lands): declines every shape so that
-// api.cu falls through to the exact fp32 CUDA-core kernels.
+// tcgen05 (5th-gen tensor core) TF32 GEMM for sm_100a: C[i,j] = sum_r A(i,r) * B(r,j), fp32 in / fp32 out,
+// operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 4-stage shared-memory ring, accumulated by
+// tcgen05.mma.kind::tf32 into TMEM, drained by 4 epilogue warps with tcgen05.ld and the same fused epilogues as
+// the CUDA-core path (bias, erf-GELU + saved pre-activation, GELU', per-sample DropPath scale, residual,
+// accumulate, split-R atomic accumulate).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+//
+// Operand layouts.  Each operand is either reduction-contiguous ("K-major": activations X[m,k], weights W[n,k])
+// or output-index-contiguous ("MN-major": needed by backward-data for W and by backward-weight for both
+// operands).  Both are fed straight from the row-major tensors -- no transposed copies:
+//   K-major : TMA box {32 r, ROWS i}  -> smem [ROWS][128 B], canonical SW128 K-major, SBO = 1024 B
+//   MN-major: TMA box {32 i, 32 r} per 32-wide index group (swizzle 128B with 32B atoms) -> smem
+//             [group][32 r][128 B], canonical SW128_BASE32B MN-major (the only MN-major layout tcgen05 takes for
+//             32-bit operands), LBO = 4096 B (group stride), SBO = 512 B (4 r-rows)
+// One MMA consumes 8 reduction elements (32 B of fp32 read as tf32): K-major advances the descriptor start
+// address by 32 B inside the swizzle atom, MN-major by 1024 B.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace mic {
-int tc_linear_fwd(const float*, int, const float*, int, int, const float*, float*, int, int, int, int, int, float*, int,
-                  const float*, int, const float*, int, int, int, cudaStream_t) {
-    return MIC_ERR_UNSUPPORTED;
+
+constexpr int TM = 128;          // output rows per CTA (UMMA M)
+constexpr int TKB = 32;          // reduction elements per stage (128 B of fp32)
+constexpr int STAGES = 3;
+constexpr int TC_THREADS = 192;
+
+struct TcEpi {
+    float* C; int64_t ldc;
+    int I, J;
+    const float* bias;
+    int act; float* pre; int64_t ldpre;
+    const float* mulgrad; int64_t ldmg;
+    const float* res; int64_t ldres;
+    const float* rowscale_i; int rps_i;
+    const float* rowscale_r; int rps_r;     // uniform per split chunk (checked on the host)
+    int accumulate;                         // 0 store, 1 +=, 2 atomicAdd
+    int kb_total, kb_per_split;
+};
+
+// optional per-CTA phase trace (debug): 16 x u64 globaltimer stamps per CTA when a buffer is registered
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+    unsigned long long* t = g_tc_trace;
+    if (t) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < 4096) t[cta * 16 + slot] = now;
+    }
 }
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout type at bits 61..63)
+// layout: 2 = SWIZZLE_128B (16-byte atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only
+// layout tcgen05 accepts for MN-major 32-bit (tf32) operands; TMA side = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+// BNT: B-tile columns (UMMA N, multiple of 16, <= 128); TCOLS: TMEM columns (power of two >= BNT)
+// EPI (compile-time epilogue kind, keeps the drain loop small and branch-free):
+//   0 plain store (+bias, *rowscale)   1 bias + save pre-activation + erf-GELU   2 residual: res + rowscale*(acc+bias)
+//   3 multiply by GELU'(aux)           4 accumulate (C += acc)                   5 atomic accumulate (split-R)
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapP, TcEpi e, int BNT,
+               int TCOLS) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = TM * TKB * 4;                     // 16 KB
+    const int b_groups = (BNT + 31) / 32;
+    const int B_BYTES = (B_MN ? b_groups * 32 : BNT) * TKB * 4;
+    const int B_STRIDE = 128 * TKB * 4;                       // fixed slot size (16 KB) keeps every slot 1024-aligned
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STRIDE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * TM, j0 = blockIdx.y * BNT;
+    const int kb0 = blockIdx.z * e.kb_per_split;
+    const int kb1 = min(e.kb_total, kb0 + e.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) trace(0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) trace(1);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            const uint32_t tx = A_BYTES + B_BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], tx);
+                const int r0 = (kb0 + kb) * TKB;
+                uint8_t* a = sA + s * A_BYTES;
+                uint8_t* b = sB + s * B_STRIDE;
+                if (A_MN) {
+#pragma unroll
+                    for (int g = 0; g < TM / 32; ++g) tma_load_2d(a + g * 4096, &mapA, &full[s], i0 + g * 32, r0);
+                } else {
+                    tma_load_2d(a, &mapA, &full[s], r0, i0);
+                }
+                if (B_MN) {
+                    for (int g = 0; g < b_groups; ++g) tma_load_2d(b + g * 4096, &mapB, &full[s], j0 + g * 32, r0);
+                } else {
+                    tma_load_2d(b, &mapB, &full[s], r0, j0);
+                }
+                if (kb == 0) trace(2);
+            }
+            trace(3);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (kb == 0) trace(4);
+                const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + s * B_STRIDE);
+#pragma unroll
+                for (int k = 0; k < TKB / 8; ++k) {
+                    // MN-major: [group][32 r][128 B]; atom = 4 r-rows (512 B): LBO = group stride, SBO = 512 B, 8 r per MMA
+                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
+                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
+                    umma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);          // frees the smem slot once these MMAs retire
+            }
+            umma_commit(tmem_full);              // accumulator complete
+            trace(5);
+        }
+    } else {
+        // ---------------- epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = output rows i0 + 32q + lane
+        const int q = warp & 3;
+        const int gi = i0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        if (warp == 2 && lane == 0) trace(6);
+        // Drain: TMEM -> registers -> fused epilogue math -> 128B-swizzled staging tile in shared memory (the operand
+        // ring is free once tmem_full fired) -> one TMA store (or TMA reduce-add for accumulate / split-R) per
+        // 32-column chunk.  TMA clips rows >= I and columns >= J, so ragged edges need no store guards.
+        const bool row_ok = gi < e.I;
+        float rs = e.rowscale_r ? e.rowscale_r[(int64_t)kb0 * TKB / e.rps_r] : 1.f;
+        if (row_ok && e.rowscale_i) rs *= e.rowscale_i[gi / e.rps_i];
+        const bool use_bias = e.bias != nullptr && blockIdx.z == 0;
+        const int64_t gi64 = gi;
+        const float* aux = nullptr;          // EPI 2: residual row, EPI 3: pre-activation row
+        if (EPI == 2) aux = e.res + gi64 * e.ldres;
+        if (EPI == 3) aux = e.mulgrad + gi64 * e.ldmg;
+        const int64_t ldaux = EPI == 2 ? e.ldres : e.ldmg;
+        const bool aux_al = aux && ((reinterpret_cast<uintptr_t>(aux) | (uintptr_t)(ldaux * 4)) & 15) == 0 && (j0 & 3) == 0;
+        const bool bias_al = use_bias && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0 && (j0 & 3) == 0;
+        const int row = q * 32 + lane;                    // row inside the 128-row tile
+        const bool want_pre = EPI == 1 && e.pre != nullptr;
+        int nchunk = 0;
+        for (int c0 = 0; c0 < BNT; c0 += 32, ++nchunk) {
+            float v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = 0.f;
+            }
+            if (c0 == 0 && warp == 2 && lane == 0) trace(10);
+            const int gj0 = j0 + c0;
+            const int ncol = min(32, min(BNT - c0, e.J - gj0));      // valid columns in this chunk (may be <= 0)
+            // staging buffers: chunk c -> 16 KB slot c of the operand ring (6 slots: sA[0..2], sB[0..2]);
+            // EPI 1 additionally stages the pre-activation in slot 3 + c (BNT <= 96 there)
+            uint8_t* cbuf = smem + nchunk * 16384;
+            uint8_t* pbuf = smem + (3 + nchunk) * 16384;
+            float4 av[8];
+            if ((EPI == 2 || EPI == 3) && row_ok) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (aux_al && 4 * t + 3 < ncol) av[t] = *reinterpret_cast<const float4*>(aux + gj0 + 4 * t);
+                    else {
+                        av[t].x = 4 * t + 0 < ncol ? aux[gj0 + 4 * t + 0] : 0.f;
+                        av[t].y = 4 * t + 1 < ncol ? aux[gj0 + 4 * t + 1] : 0.f;
+                        av[t].z = 4 * t + 2 < ncol ? aux[gj0 + 4 * t + 2] : 0.f;
+                        av[t].w = 4 * t + 3 < ncol ? aux[gj0 + 4 * t + 3] : 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) av[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float x[4] = {v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]};
+                if (use_bias) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias_al && 4 * t + 3 < ncol) b4 = *reinterpret_cast<const float4*>(e.bias + gj0 + 4 * t);
+                    else {
+                        if (4 * t + 0 < ncol) b4.x = e.bias[gj0 + 4 * t + 0];
+                        if (4 * t + 1 < ncol) b4.y = e.bias[gj0 + 4 * t + 1];
+                        if (4 * t + 2 < ncol) b4.z = e.bias[gj0 + 4 * t + 2];
+                        if (4 * t + 3 < ncol) b4.w = e.bias[gj0 + 4 * t + 3];
+                    }
+                    x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+                }
+                const uint32_t soff = (uint32_t)row * 128u + ((uint32_t)(t ^ (row & 7)) << 4);
+                if (EPI == 1) {
+                    if (want_pre) *reinterpret_cast<float4*>(pbuf + soff) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = gelu_erf(x[u]);
+                }
+                if (EPI == 3) {
+                    x[0] *= gelu_erf_grad(av[t].x); x[1] *= gelu_erf_grad(av[t].y);
+                    x[2] *= gelu_erf_grad(av[t].z); x[3] *= gelu_erf_grad(av[t].w);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] *= rs;
+                if (EPI == 2) { x[0] += av[t].x; x[1] += av[t].y; x[2] += av[t].z; x[3] += av[t].w; }
+                *reinterpret_cast<float4*>(cbuf + soff) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0 && ncol > 0) {
+                if (EPI == 4 || EPI == 5) tma_reduce_add_2d(&mapC, cbuf, gj0, i0);
+                else tma_store_2d(&mapC, cbuf, gj0, i0);
+                if (want_pre) tma_store_2d(&mapP, pbuf, gj0, i0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (warp == 2 && lane == 0) trace(7);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 32) trace(8);
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+    }
+    if (threadIdx.x == 32) trace(9);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent d0, outer extent d1 with row stride ld (floats)
+static bool make_map(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0, uint32_t box1,
+                     bool atom32) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct TcOperand {
+    const float* p;
+    bool mn_major;     // true: output index contiguous, rows = reduction index
+    int64_t ld;        // row stride in floats
+};
+
+static bool operand_ok(const TcOperand& o) { return (reinterpret_cast<uintptr_t>(o.p) & 15) == 0 && o.ld % 4 == 0 && o.ld > 0; }
+
+// generic launcher: C[I,J] = sum_R A(i,r) B(r,j)
+static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int kb_per_split, cudaStream_t st) {
+    if (!operand_ok(A) || !operand_ok(B)) return MIC_ERR_UNSUPPORTED;
+    const int I = e.I, J = e.J;
+    int BNT = J <= 128 ? ((J + 15) / 16) * 16 : 128;
+    if (J > 128) {   // balance column tiles (e.g. 192 -> 2 x 96); multiples of 32 so that no 32-column store box
+                     // straddles two tiles
+        const int nt = (J + 127) / 128;
+        BNT = (((J + nt - 1) / nt) + 31) / 32 * 32;
+    }
+    int epi = 0;
+    if (e.accumulate == 2) epi = 5;
+    else if (e.accumulate == 1) epi = 4;
+    else if (e.act == 1) epi = 1;
+    else if (e.res) epi = 2;
+    else if (e.mulgrad) epi = 3;
+    if (epi == 1 && BNT > 96) {       // the pre-activation needs its own staging slots: at most 3 chunks per tile
+        const int nt = (J + 95) / 96;
+        BNT = nt > 1 ? (((J + nt - 1) / nt) + 31) / 32 * 32 : BNT;
+    }
+    int TCOLS = 32;
+    while (TCOLS < BNT) TCOLS <<= 1;
+    if ((reinterpret_cast<uintptr_t>(e.C) & 15) || e.ldc % 4) return MIC_ERR_UNSUPPORTED;
+    if (epi == 1 && e.pre && ((reinterpret_cast<uintptr_t>(e.pre) & 15) || e.ldpre % 4)) return MIC_ERR_UNSUPPORTED;
+    CUtensorMap mA, mB, mC, mP;
+    bool ok = A.mn_major ? make_map(&mA, A.p, (uint64_t)I, (uint64_t)R, (uint64_t)A.ld, 32, TKB, true)
+                         : make_map(&mA, A.p, (uint64_t)R, (uint64_t)I, (uint64_t)A.ld, TKB, TM, false);
+    ok = ok && (B.mn_major ? make_map(&mB, B.p, (uint64_t)J, (uint64_t)R, (uint64_t)B.ld, 32, TKB, true)
+                           : make_map(&mB, B.p, (uint64_t)R, (uint64_t)J, (uint64_t)B.ld, TKB, (uint32_t)BNT, false));
+    ok = ok && make_map(&mC, e.C, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldc, 32, TM, false);
+    if (ok && epi == 1 && e.pre) ok = make_map(&mP, e.pre, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldpre, 32, TM, false);
+    else mP = mC;
+    if (!ok) return MIC_ERR_UNSUPPORTED;
+    e.kb_total = (R + TKB - 1) / TKB;
+    e.kb_per_split = (kb_per_split > 0 && kb_per_split < e.kb_total) ? kb_per_split : e.kb_total;
+    const int splits = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
+    const size_t smem = 1024 + (size_t)STAGES * (TM * TKB * 4 + 128 * TKB * 4) + 256;
+    dim3 grid((I + TM - 1) / TM, (J + BNT - 1) / BNT, splits);
+#define LAUNCH(AM, BM_, EP)                                                                                      \
+    do {                                                                                                         \
+        static bool attr_done = false;                                                                           \
+        if (!attr_done) {                                                                                        \
+            cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr_done = true;                                                                                    \
+        }                                                                                                        \
+        gemm_tc_kernel<AM, BM_, EP><<<grid, TC_THREADS, smem, st>>>(mA, mB, mC, mP, e, BNT, TCOLS);                       \
+    } while (0)
+#define LAUNCH_EPI(AM, BM_)                                                            \
+    switch (epi) {                                                                     \
+        case 0: LAUNCH(AM, BM_, 0); break;                                             \
+        case 1: LAUNCH(AM, BM_, 1); break;                                             \
+        case 2: LAUNCH(AM, BM_, 2); break;                                             \
+        case 3: LAUNCH(AM, BM_, 3); break;                                             \
+        case 4: LAUNCH(AM, BM_, 4); break;                                             \
+        default: LAUNCH(AM, BM_, 5); break;                                            \
+    }
+    if (!A.mn_major && !B.mn_major) { LAUNCH_EPI(false, false) }
+    else if (!A.mn_major && B.mn_major) { LAUNCH_EPI(false, true) }
+    else if (A.mn_major && B.mn_major) { LAUNCH(true, true, 5); }
+    else return MIC_ERR_UNSUPPORTED;
+#undef LAUNCH_EPI
+#undef LAUNCH
+    return check_launch("gemm_tc_kernel");
+}
+
+int colsum(const float* X, int64_t ldx, int M, int N, const float* rowscale, int rps, float* out, cudaStream_t st);
+
+}  // namespace mic
+extern "C" int mic_debug_tc_trace(void* buf) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(mic::g_tc_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+namespace mic {
+
+int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn, const float* bias, float* Y, int ldy,
+                  int M, int N, int K, int act, float* pre, int ldpre, const float* res, int ldres, const float* rowscale,
+                  int rps, int accumulate, int mode, cudaStream_t st) {
+    (void)mode;
+    if (N < 16 || K < 8) return MIC_ERR_UNSUPPORTED;
+    TcEpi e{};
+    e.C = Y; e.ldc = ldy; e.I = M; e.J = N; e.bias = bias; e.act = act; e.pre = pre; e.ldpre = ldpre; e.res = res;
+    e.ldres = ldres; e.rowscale_i = rowscale; e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
+    TcOperand A{X, false, ldx};
+    TcOperand B{W, w_is_kn != 0, ldw};      // W[n,k]: K-major; W[k,n]: MN-major
+    return tc_gemm(A, B, e, K, 0, st);
+}
+
+int tc_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int w_is_kn, float* dX, int lddx, int M, int N,
+                       int K, const float* gelu_pre, int ldpre, const float* rowscale, int rps, int accumulate, int mode,
+                       cudaStream_t st) {
+    (void)mode;
+    if (K < 16 || N < 8) return MIC_ERR_UNSUPPORTED;
+    TcEpi e{};
+    e.C = dX; e.ldc = lddx; e.I = M; e.J = K; e.mulgrad = gelu_pre; e.ldmg = ldpre; e.rowscale_i = rowscale;
+    e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
+    TcOperand A{dY, false, lddy};
+    // B(r = n, j = k): W[n,k] has j contiguous -> MN-major; W[k,n] has r contiguous -> K-major
+    TcOperand B{W, w_is_kn == 0, ldw};
+    return tc_gemm(A, B, e, N, 0, st);
+}
+
+int tc_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int w_is_kn, float* db,
+                         int M, int N, int K, const float* rowscale, int rps, int mode, cudaStream_t st) {
+    (void)mode;
+    if (N < 16 || K < 16) return MIC_ERR_UNSUPPORTED;
+    TcEpi e{};
+    e.C = dW; e.ldc = lddw; e.accumulate = 2;
+    TcOperand A{}, B{};
+    if (!w_is_kn) { A = {dY, true, lddy}; B = {X, true, ldx}; e.I = N; e.J = K; }
+    else { A = {X, true, ldx}; B = {dY, true, lddy}; e.I = K; e.J = N; }
+    const int kb_total = (M + TKB - 1) / TKB;
+    const int BNT = e.J <= 128 ? e.J : 128;
+    const int tiles = ((e.I + TM - 1) / TM) * ((e.J + BNT - 1) / BNT);
+    int splits = (num_sms() * 2 + tiles - 1) / tiles;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    int kb_per = (kb_total + splits - 1) / splits;
+    if (rowscale) {
+        // the DropPath scale must be uniform inside a split chunk: chunk rows must divide rows-per-sample
+        if (rps <= 0 || rps % TKB) return MIC_ERR_UNSUPPORTED;
+        const int kb_rps = rps / TKB;
+        if (kb_per > kb_rps) kb_per = kb_rps;
+        while (kb_rps % kb_per) --kb_per;
+        e.rowscale_r = rowscale; e.rps_r = rps;
+    }
+    int rc = tc_gemm(A, B, e, M, kb_per, st);
+    if (rc) return rc;
+    if (db) return colsum(dY, lddy, M, N, rowscale, rps > 0 ? rps : 1, db, st);
+    return MIC_OK;
+}
+
 }  // namespace mic

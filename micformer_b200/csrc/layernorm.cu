@@ -170,7 +170,7 @@ extern "C" int mic_layernorm_bwd(const float* dy, const float* x0, int C0, const
     const int64_t prows = (int64_t)B * Dp * Hp * Wp;
     LnGeom g{B, D, H, W, Dp, Hp, Wp};
     const int wpb = 8;
-    int64_t blocks = ceil_div64(prows, (int64_t)wpb * 8);
+    int64_t blocks = ceil_div64(prows, (int64_t)wpb * 2);
     const int64_t cap = (int64_t)num_sms() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
