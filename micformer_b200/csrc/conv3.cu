@@ -386,11 +386,13 @@ extern "C" int mic_conv3_bwd_weight(const float* dy, const float* x0, int C0, co
     cudaStream_t st = (cudaStream_t)stream;
     if (Co <= 8) {
         const size_t smem = (NH * 33 + NB * 8) * sizeof(float);
-        cudaFuncSetAttribute(conv3_bwd_weight_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static bool once8 = false;
+        if (!once8) { cudaFuncSetAttribute(conv3_bwd_weight_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once8 = true; }
         conv3_bwd_weight_kernel<8><<<grid, 64, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     } else {
         const size_t smem = (NH * 33 + NB * 16) * sizeof(float);
-        cudaFuncSetAttribute(conv3_bwd_weight_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static bool once16 = false;
+        if (!once16) { cudaFuncSetAttribute(conv3_bwd_weight_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once16 = true; }
         conv3_bwd_weight_kernel<16><<<grid, 128, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     }
     return check_launch("conv3_bwd_weight_kernel");

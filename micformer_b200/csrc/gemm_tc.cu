@@ -37,6 +37,8 @@ struct TcEpi {
     const float* rowscale_r; int rps_r;     // uniform per split chunk (checked on the host)
     int accumulate;                         // 0 store, 1 +=, 2 atomicAdd
     int kb_total, kb_per_split;
+    int round_rn;                           // 1: operands rounded to nearest TF32 in shared memory before the MMA
+                                            // (the tensor core itself truncates; truncation is biased toward zero)
 };
 
 // optional per-CTA phase trace (debug): 16 x u64 globaltimer stamps per CTA when a buffer is registered
@@ -145,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* conv = tmem_full + 2;          // [STAGES] operands rounded (arrived by the 4 converter warps)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * TM, j0 = blockIdx.y * BNT;
@@ -154,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (threadIdx.x == 0) trace(0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+                mbar_wait(e.round_rn ? &conv[s] : &full[s], ph);
                 tc_fence_after();
                 if (kb == 0) trace(4);
                 const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
@@ -225,6 +228,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ---------------- epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = output rows i0 + 32q + lane
         const int q = warp & 3;
         const int gi = i0 + q * 32 + lane;
+        if (e.round_rn) {
+            // converter role during the main loop: round the freshly landed A/B tiles to nearest-even TF32 in
+            // place (element-wise, so the swizzle is irrelevant), then hand the stage to the MMA warp
+            const int et = (warp - 2) * 32 + lane;                       // 0..127
+            const int b_vec = B_BYTES / 16;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                float4* a4 = reinterpret_cast<float4*>(sA + s * A_BYTES);
+                float4* b4 = reinterpret_cast<float4*>(sB + s * B_STRIDE);
+#pragma unroll 4
+                for (int i = et; i < A_BYTES / 16; i += 128) {
+                    float4 t = a4[i];
+                    uint32_t r0, r1, r2, r3;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(t.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(t.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(t.z));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(t.w));
+                    a4[i] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+                }
+                for (int i = et; i < b_vec; i += 128) {
+                    float4 t = b4[i];
+                    uint32_t r0, r1, r2, r3;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(t.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(t.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(t.z));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(t.w));
+                    b4[i] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
+            }
+        }
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
@@ -454,6 +492,7 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
     TcEpi e{};
     e.C = Y; e.ldc = ldy; e.I = M; e.J = N; e.bias = bias; e.act = act; e.pre = pre; e.ldpre = ldpre; e.res = res;
     e.ldres = ldres; e.rowscale_i = rowscale; e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
+    e.round_rn = 1;       // forward GEMMs carry the logits parity bar: unbiased TF32 rounding
     TcOperand A{X, false, ldx};
     TcOperand B{W, w_is_kn != 0, ldw};      // W[n,k]: K-major; W[k,n]: MN-major
     return tc_gemm(A, B, e, K, 0, st);

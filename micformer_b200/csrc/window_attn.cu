@@ -246,7 +246,11 @@ static int launch_fwd(const float* q, int ldq, const float* k, const float* v, i
     auto kern = window_attn_fwd_kernel<HD>;
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) return fail(MIC_ERR_UNSUPPORTED, "window_attn_fwd: window too large for shared memory");
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static size_t granted = 0;      // per instantiation; raise the opt-in limit only when it grows
+        if (smem > granted) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            granted = smem;
+        }
     }
     const int threads = ceil_div(g.G * g.N, 32) * 32;
     const int64_t blocks = ceil_div64(g.ngroups, g.G);
@@ -262,7 +266,11 @@ static int launch_bwd(const float* q, int ldq, const float* k, const float* v, i
     auto kern = window_attn_bwd_kernel<HD>;
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) return fail(MIC_ERR_UNSUPPORTED, "window_attn_bwd: window too large for shared memory");
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static size_t granted = 0;
+        if (smem > granted) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            granted = smem;
+        }
     }
     const int threads = ceil_div(g.G * g.N, 32) * 32;
     const int64_t blocks = ceil_div64(g.ngroups, g.G);

@@ -51,6 +51,15 @@ def _drop_scale(mod, batch, device):
     return mod.sample_scale(batch, device) if isinstance(mod, DropPath) else None
 
 
+def _block_scales(block, batch, device):
+    """Per-sample DropPath scales of a block's two residual branches: pre-drawn in one shot by the enclosing
+    MicFormer (``_predraw_drop_path``) or drawn here when the block is used stand-alone."""
+    pre = block.__dict__.pop("_dp_scales", None)
+    if pre is not None:
+        return pre
+    return _drop_scale(block.drop_path, batch, device), _drop_scale(block.drop_path, batch, device)
+
+
 class Mlp(nn.Module):
     """M:16-34.  Parameter container; fused as LN -> fc1 -> GELU -> fc2 -> +residual inside the block ops."""
 
@@ -246,9 +255,7 @@ class CrossTransformerBlock3D(nn.Module):
         self.stn = SpatialTransformer()
 
     def forward(self, x, xa):
-        B = x.shape[0]
-        s1 = _drop_scale(self.drop_path, B, x.device)
-        s2 = _drop_scale(self.drop_path, B, x.device)
+        s1, s2 = _block_scales(self, x.shape[0], x.device)
         a = self.cross_attn
         co = self.conv_offset
         cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
@@ -286,9 +293,7 @@ class TransformerBlock3D(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        B = x.shape[0]
-        s1 = _drop_scale(self.drop_path, B, x.device)
-        s2 = _drop_scale(self.drop_path, B, x.device)
+        s1, s2 = _block_scales(self, x.shape[0], x.device)
         a = self.self_attn
         return ops.SelfBlockFn.apply(
             x.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
@@ -432,8 +437,24 @@ class MicFormer(nn.Module):
         self.reverse_patch_embedding = nn.ConvTranspose3d(2 * embed_dim, embed_dim // 2, (4, 4, 4), stride=4)
 
     # -- pieces -------------------------------------------------------------------------------------------
+    def _predraw_drop_path(self, batch, device):
+        """Training mode: draw the Bernoulli(keep)/keep scales of ALL blocks' two residual branches with three
+        torch kernels (one rand, one compare, one divide) instead of two tiny kernels per branch."""
+        blocks = [b for b in self.modules() if isinstance(b, (CrossTransformerBlock3D, TransformerBlock3D))
+                  and isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0.0]
+        if not blocks or not self.training:
+            return
+        keep = getattr(self, "_dp_keep", None)
+        if keep is None or keep.device != device or keep.numel() != len(blocks):
+            keep = torch.tensor([1.0 - b.drop_path.drop_prob for b in blocks], device=device).view(-1, 1, 1)
+            self.__dict__["_dp_keep"] = keep
+        scales = (torch.rand(len(blocks), 2, batch, device=device) < keep).float() / keep
+        for i, b in enumerate(blocks):
+            b.__dict__["_dp_scales"] = (scales[i, 0], scales[i, 1])
+
     def _trunk(self, vol):
         """Everything up to (not including) cat -> norm2 -> reverse_patch_embedding; vol is (B, 2, D, H, W)."""
+        self._predraw_drop_path(vol.shape[0], vol.device)
         moving = self.patch_embed(vol, 0)
         fixed = self.patch_embed(vol, 1)
         feats_m, feats_f = [], []

@@ -33,7 +33,35 @@ def _empty(shape, like: Tensor) -> Tensor:
     return torch.empty(shape, device=like.device, dtype=torch.float32)
 
 
+# Zero-initialised gradient buffers (atomically accumulated by the kernels) are carved out of ONE zero-filled
+# arena per backward call: one fill kernel instead of ~20 per block.
+_arena = None
+
+
+class zero_arena:
+    def __init__(self, nfloats: int, like: Tensor):
+        self.n, self.like = int(nfloats), like
+
+    def __enter__(self):
+        global _arena
+        self.prev = _arena
+        _arena = [torch.zeros(self.n, device=self.like.device, dtype=torch.float32), 0]
+
+    def __exit__(self, *exc):
+        global _arena
+        _arena = self.prev
+
+
 def _zeros(shape, like: Tensor) -> Tensor:
+    n = 1
+    for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+        n *= d
+    if _arena is not None:
+        off = _arena[1]
+        end = off + ((n + 63) // 64) * 64            # 256-byte aligned slices (TMA / float4 friendly)
+        if end <= _arena[0].numel():
+            _arena[1] = end
+            return _arena[0][off:off + n].view(shape)
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
 
@@ -259,14 +287,15 @@ class SelfBlockFn(torch.autograd.Function):
         C = x.shape[-1]
         P = B * pdims[0] * pdims[1] * pdims[2]
         dy = dy.contiguous()
-        dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-        do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
-        dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
-        dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
-        linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
-        dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
-        dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
-        dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+        with zero_arena(12 * C * C + 128 * C + 4096, x):
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+            do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+            dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+            dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
+            linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
+            dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
+            dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
+            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
         return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
                 df2b)
 
@@ -329,27 +358,28 @@ class CrossBlockFn(torch.autograd.Function):
         P = B * Dp * Hp * Wp
         HC = cw.shape[-1]
         dy = dy.contiguous()
-        dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-        do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
-        dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
-        dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
-        dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
-        dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
-        dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
-        dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
-        dpos = _empty((P, 3), x)
-        N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa_p), N.ptr(pos), N.ptr(dxa_p), N.ptr(dpos), B, Dp, Hp, Wp, Dp,
-               Hp, Wp, C)
-        dh16 = _empty((P, HC), x)
-        dlnw = _zeros((HC,), x); dlnb = _zeros((HC,), x); dw3 = _zeros((3, HC), x)
-        N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
-               N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
-        N.call("mic_conv3_bwd_data", N.ptr(dh16), N.ptr(cw), N.ptr(dxn_p), C, 1, N.ptr(dxa_p), C, 1, B, Dp, Hp, Wp, Dp, Hp,
-               Wp, HC, 0)
-        dcw = torch.zeros_like(cw); dcb = _zeros((HC,), x)
-        N.call("mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp, Hp, Wp,
-               Dp, Hp, Wp, HC, 0)
-        dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+        with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x):
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+            do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+            dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+            dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
+            dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
+            dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
+            dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
+            dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
+            dpos = _empty((P, 3), x)
+            N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa_p), N.ptr(pos), N.ptr(dxa_p), N.ptr(dpos), B, Dp, Hp, Wp, Dp,
+                   Hp, Wp, C)
+            dh16 = _empty((P, HC), x)
+            dlnw = _zeros((HC,), x); dlnb = _zeros((HC,), x); dw3 = _zeros((3, HC), x)
+            N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
+                   N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
+            N.call("mic_conv3_bwd_data", N.ptr(dh16), N.ptr(cw), N.ptr(dxn_p), C, 1, N.ptr(dxa_p), C, 1, B, Dp, Hp, Wp, Dp, Hp,
+                   Wp, HC, 0)
+            dcw = torch.zeros_like(cw); dcb = _zeros((HC,), x)
+            N.call("mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp, Hp, Wp,
+                   Dp, Hp, Wp, HC, 0)
+            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
         if padded:
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
         else:
