@@ -1,0 +1,1 @@
+from micformer_b200.models.MICFormer_self import *  # noqa: F401,F403
