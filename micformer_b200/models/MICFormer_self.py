@@ -47,6 +47,19 @@ class DropPath(nn.Module):
         return f"drop_prob={round(self.drop_prob, 3):0.3f}"
 
 
+import os as _os
+
+_TWO_STREAMS = _os.environ.get("MICFORMER_TWO_STREAMS", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(device):
+    st = _SIDE.get(device)
+    if st is None:
+        st = _SIDE[device] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _drop_scale(mod, batch, device):
     return mod.sample_scale(batch, device) if isinstance(mod, DropPath) else None
 
@@ -358,12 +371,44 @@ class BasicLayer(nn.Module):
             self.downsample = downsample(dim=dim, norm_layer=norm_layer)
 
     def forward(self, x, xa):
+        if not (_TWO_STREAMS and x.is_cuda):
+            for i in range(len(self.blocks1)):
+                x, xa = self.self_blocks1[i](x), self.self_blocks2[i](xa)
+                x, xa = self.blocks1[i](x, xa), self.blocks2[i](xa, x)
+            if self.downsample is not None:
+                return x, xa, self.downsample(x), self.downsample(xa)
+            return x, xa, x, xa
+        # The CT branch runs on the current stream, the MR branch on a side stream: the two self blocks, the two
+        # cross blocks (both read the pre-update pair, M:700-701) and the two shared-sampler calls are independent,
+        # and at batch 2 the deep stages are latency-bound (8..48 CTAs per kernel on 148 SMs).  Inside a captured
+        # CUDA graph the two streams become parallel branches; autograd replays each backward on its forward stream.
+        main = torch.cuda.current_stream()
+        side = _side_stream(x.device)
+
+        def on_side(fn, *args):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = fn(*args)
+            for a in args:                 # inputs allocated on `main`, consumed on `side`
+                a.record_stream(side)
+            return out
+
         for i in range(len(self.blocks1)):
-            x, xa = self.self_blocks1[i](x), self.self_blocks2[i](xa)
-            x, xa = self.blocks1[i](x, xa), self.blocks2[i](xa, x)
-        if self.downsample is not None:
-            return x, xa, self.downsample(x), self.downsample(xa)
-        return x, xa, x, xa
+            xa_s = on_side(self.self_blocks2[i], xa)
+            x_s = self.self_blocks1[i](x)
+            main.wait_stream(side)
+            xa_s.record_stream(main)
+            xa = on_side(self.blocks2[i], xa_s, x_s)
+            x = self.blocks1[i](x_s, xa_s)
+            main.wait_stream(side)
+            xa.record_stream(main)
+        if self.downsample is None:
+            return x, xa, x, xa
+        xa_d = on_side(self.downsample, xa)
+        x_d = self.downsample(x)
+        main.wait_stream(side)
+        xa_d.record_stream(main)
+        return x, xa, x_d, xa_d
 
 
 class PatchEmbed3D(nn.Module):

@@ -66,6 +66,54 @@ def _zeros(shape, like: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# weight-gradient side branch: dW / db kernels do not feed the data-gradient chain, so each backward forks them
+# onto an auxiliary stream (one per calling stream) and joins before returning.  Under CUDA-graph capture this
+# becomes a parallel branch; buffers are allocated on the calling stream before the fork and the join precedes
+# any later reuse, so no record_stream bookkeeping is needed.
+# ----------------------------------------------------------------------------------------------------------
+import os as _os
+
+_AUX_ON = _os.environ.get("MICFORMER_AUX_STREAM", "1") != "0"
+_AUX = {}
+
+
+class side_branch:
+    """with side_branch() as sb: sb.run(fn, *args) ... ; joins on exit"""
+
+    def __enter__(self):
+        self.cur = torch.cuda.current_stream()
+        self.used = False
+        self.keep = []          # inputs of side-branch kernels stay referenced until the join: the caching
+                                # allocator must not hand their memory to later main-branch kernels
+        if _AUX_ON:
+            key = (self.cur.device_index, self.cur.cuda_stream)
+            aux = _AUX.get(key)
+            if aux is None:
+                aux = _AUX[key] = torch.cuda.Stream(device=self.cur.device)
+            self.aux = aux
+        else:
+            self.aux = None
+        return self
+
+    def run(self, fn, *args, **kw):
+        if self.aux is None:
+            return fn(*args, **kw)
+        self.aux.wait_stream(self.cur)
+        with torch.cuda.stream(self.aux):
+            out = fn(*args, **kw)
+        self.used = True
+        return out
+
+    def hold(self, *tensors):
+        self.keep.extend(t for t in tensors if t is not None)
+
+    def __exit__(self, *exc):
+        if self.aux is not None and self.used:
+            self.cur.wait_stream(self.aux)
+        self.keep.clear()
+
+
+# ----------------------------------------------------------------------------------------------------------
 # thin kernel wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------------------
 def ln_fwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, beta: Tensor, dims, pdims=None):
@@ -144,6 +192,18 @@ def linear_bwd_weight(dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: 
     return dW, db
 
 
+def linear_bwd_weight_side(sb: "side_branch", dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: int, K: int, **kw):
+    """linear_bwd_weight on the side branch; outputs are allocated (zeroed) on the calling stream first."""
+    w_is_kn = kw.get("w_is_kn", False)
+    if kw.get("dW") is None:
+        kw["dW"] = _zeros((K, Nout) if w_is_kn else (Nout, K), dY)
+        kw["lddw"] = Nout if w_is_kn else K
+    if kw.get("db") is None and kw.get("want_bias", True):
+        kw["db"] = _zeros((Nout,), dY)
+    sb.hold(dY, X, kw.get("rowscale"))
+    return sb.run(linear_bwd_weight, dY, lddy, X, ldx, M, Nout, K, **kw)
+
+
 def window_attn_fwd(qkv: Tensor, C: int, heads: int, B: int, pdims, ws):
     """qkv (P, 3C) rows on the padded grid -> o (P, C), lse (P, heads)."""
     Dp, Hp, Wp = pdims
@@ -202,19 +262,19 @@ def _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded):
     return crop_add(x, pr, s1, dims, pdims)
 
 
-def _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded):
+def _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded):
     """-> do_p (P,C), dpw, dpb"""
     B, D, H, W = dims
     C = dx1.shape[-1]
     if not padded:
         T = B * D * H * W
+        dpw, dpb = linear_bwd_weight_side(sb, dx1, C, o_p, C, T, C, C, rowscale=s1, rps=D * H * W)
         do_p = linear_bwd_data(dx1, C, pw, T, C, C, rowscale=s1, rps=D * H * W)
-        dpw, dpb = linear_bwd_weight(dx1, C, o_p, C, T, C, C, rowscale=s1, rps=D * H * W)
         return do_p, dpw, dpb
     P = B * pdims[0] * pdims[1] * pdims[2]
     dpr = crop_bwd(dx1, s1, dims, pdims)
+    dpw, dpb = linear_bwd_weight_side(sb, dpr, C, o_p, C, P, C, C)
     do_p = linear_bwd_data(dpr, C, pw, P, C, C)
-    dpw, dpb = linear_bwd_weight(dpr, C, o_p, C, P, C, C)
     return do_p, dpw, dpb
 
 
@@ -230,7 +290,7 @@ def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims):
     return y, (xn2, mean2, rstd2, hpre, h)
 
 
-def _mlp_bwd(dy, x1, saved, n2w, f1w, f2w, s2, dims):
+def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims):
     """-> dx1 (= dy + grad through LN/MLP), dn2w, dn2b, df1w, df1b, df2w, df2b"""
     xn2, mean2, rstd2, hpre, h = saved
     B, D, H, W = dims
@@ -238,10 +298,10 @@ def _mlp_bwd(dy, x1, saved, n2w, f1w, f2w, s2, dims):
     T = B * D * H * W
     Hd = f1w.shape[0]
     rps = D * H * W
+    df2w, df2b = linear_bwd_weight_side(sb, dy, C, h, Hd, T, C, Hd, rowscale=s2, rps=rps)
     dh = linear_bwd_data(dy, C, f2w, T, C, Hd, gelu_pre=hpre, rowscale=s2, rps=rps)
-    df2w, df2b = linear_bwd_weight(dy, C, h, Hd, T, C, Hd, rowscale=s2, rps=rps)
+    df1w, df1b = linear_bwd_weight_side(sb, dh, Hd, xn2, C, T, Hd, C)
     dxn2 = linear_bwd_data(dh, Hd, f1w, T, Hd, C)
-    df1w, df1b = linear_bwd_weight(dh, Hd, xn2, C, T, Hd, C)
     dx1, _, dn2w, dn2b = ln_bwd(dxn2, x1, None, n2w, mean2, rstd2, dy, None, dims)
     return dx1, dn2w, dn2b, df1w, df1b, df2w, df2b
 
@@ -287,14 +347,14 @@ class SelfBlockFn(torch.autograd.Function):
         C = x.shape[-1]
         P = B * pdims[0] * pdims[1] * pdims[2]
         dy = dy.contiguous()
-        with zero_arena(12 * C * C + 128 * C + 4096, x):
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-            do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+        with zero_arena(12 * C * C + 128 * C + 4096, x), side_branch() as sb:
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C)
+            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
             dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
             linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
-            dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
-            dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
         return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
                 df2b)
@@ -358,14 +418,14 @@ class CrossBlockFn(torch.autograd.Function):
         P = B * Dp * Hp * Wp
         HC = cw.shape[-1]
         dy = dy.contiguous()
-        with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x):
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-            do_p, dpw, dpb = _proj_residual_bwd(dx1, o_p, pw, s1, dims, pdims, padded)
+        with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x), side_branch() as sb:
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
+            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C)
+            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
             dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
             dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
-            dqw, dqb = linear_bwd_weight(dqkv, 3 * C, xn_p, C, P, C, C)
-            dkvw, dkvb = linear_bwd_weight(dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
             dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
             dpos = _empty((P, 3), x)
             N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa_p), N.ptr(pos), N.ptr(dxa_p), N.ptr(dpos), B, Dp, Hp, Wp, Dp,
@@ -374,11 +434,12 @@ class CrossBlockFn(torch.autograd.Function):
             dlnw = _zeros((HC,), x); dlnb = _zeros((HC,), x); dw3 = _zeros((3, HC), x)
             N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
                    N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
+            dcw = _zeros(tuple(cw.shape), x); dcb = _zeros((HC,), x)
+            sb.hold(dh16, xn_p, xa_p)
+            sb.run(N.call, "mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp,
+                   Hp, Wp, Dp, Hp, Wp, HC, 0)
             N.call("mic_conv3_bwd_data", N.ptr(dh16), N.ptr(cw), N.ptr(dxn_p), C, 1, N.ptr(dxa_p), C, 1, B, Dp, Hp, Wp, Dp, Hp,
                    Wp, HC, 0)
-            dcw = torch.zeros_like(cw); dcb = _zeros((HC,), x)
-            N.call("mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp, Hp, Wp,
-                   Dp, Hp, Wp, HC, 0)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
         if padded:
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
