@@ -95,6 +95,13 @@ int mic_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int
 int mic_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
                          int B, int D, int H, int W, int Dp, int Hp, int Wp, int Co, int dy_ncdhw, void* stream);
 
+/* tcgen05 implicit-GEMM forward of the same convolution (TF32 tensor cores, fp32 accumulate in TMEM): a CTA owns an
+ * 8x16 x/y footprint, marches over z and reads all 27 taps as shifted views of z-planes staged once in shared memory.
+ * Wk is the weight permuted to [27][Co][C0+C1]; input grid == output grid, W % 8 == 0 and H % 16 == 0, else
+ * MIC_ERR_UNSUPPORTED is returned and the caller uses mic_conv3_fwd. */
+int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias, float* y,
+                     int B, int D, int H, int W, int Co, int out_ncdhw, void* stream);
+
 /* ---- Offset head: LayerNormProxy(16) -> GELU -> Conv3d(16->3,k1,no bias) -> + reference points
  *      (:315-317, :326-337, :360-364).  h (P,HC) -> pos (P,3) with P = B*Dp*Hp*Wp. */
 int mic_offset_head_fwd(const float* h, const float* gamma, const float* beta, const float* w3, float* pos, int B,

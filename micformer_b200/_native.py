@@ -31,6 +31,7 @@ SIGNATURES = {
     "mic_window_attn_fwd": [P, I, P, P, I, P, I, P, I, I, I, I, I, I, I, I, I, F, P],
     "mic_window_attn_bwd": [P, I, P, P, I, P, P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, I, F, P],
     "mic_conv3_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
     "mic_conv3_bwd_data": [P, P, P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "mic_conv3_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
     "mic_offset_head_fwd": [P, P, P, P, P, I, I, I, I, I, F, P],
@@ -108,6 +109,8 @@ COST = {
                                                                    (1 + (a[10] is not None)))),
     "mic_linear_bwd_weight": lambda a: (2 * a[8] * a[9] * a[10], 4 * (a[8] * a[9] + a[8] * a[10] + a[9] * a[10])),
     "mic_conv3_fwd": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[1] + a[3], a[14]),
+    "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
+    "mic_conv3_tc_fwd": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[8], a[9], a[10], a[1] + a[3], a[11]),
     "mic_conv3_bwd_data": lambda a: _cost_conv3(a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[3] + a[6], a[15]),
     "mic_conv3_bwd_weight": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[2] + a[4], a[14]),
     "mic_window_attn_fwd": lambda a: (4 * _prod(*a[8:12]) * a[12] * a[13] * _prod(*a[14:17]),
@@ -134,6 +137,8 @@ TAG = {
     "mic_linear_bwd_data": lambda a: f"M{a[7]}xN{a[8]}xK{a[9]}",
     "mic_linear_bwd_weight": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",
     "mic_conv3_fwd": lambda a: f"Cin{a[1] + a[3]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
+    "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
+    "mic_conv3_tc_fwd": lambda a: f"Cin{a[1] + a[3]}xCo{a[11]}@{a[7] * a[8] * a[9] * a[10]}",
     "mic_conv3_bwd_data": lambda a: f"Cin{a[3] + a[6]}xCo{a[15]}@{a[8] * a[12] * a[13] * a[14]}",
     "mic_conv3_bwd_weight": lambda a: f"Cin{a[2] + a[4]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
 }
@@ -176,6 +181,19 @@ def call(name: str, *args):
         rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def try_call(name: str, *args) -> bool:
+    """Like ``call`` but returns False when the entry point declines the shape (MIC_ERR_UNSUPPORTED)."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc == -2:
+        return False
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    if _prof is not None:
+        pass
+    return True
 
 
 def check_cuda_f32(*tensors):

@@ -272,11 +272,14 @@ class CrossTransformerBlock3D(nn.Module):
         a = self.cross_attn
         co = self.conv_offset
         cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
+        cwk = None
+        if ops.N.get_gemm_mode() == 1:      # tcgen05 forward reads the weight as [tap][out][in]
+            cwk = co[0].weight.detach().permute(2, 3, 4, 0, 1).reshape(27, self.hidden_channels, 2 * self.dim).contiguous()
         w3 = co[3].weight.reshape(3, self.hidden_channels)
         return ops.CrossBlockFn.apply(
             x.contiguous(), xa.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
-            a.proj.bias, cw, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
+            a.proj.bias, cw, cwk, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
             self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
 
 
@@ -542,7 +545,7 @@ class MicFormer(nn.Module):
         if Ch > 16:
             raise NotImplementedError("MicFormer.forward stand-alone needs E/2 <= 16; use Head (fused tail) instead")
         bo = torch.zeros(Ch, device=vol.device)
-        return ops.SegHeadFn.apply(m, f, self.norm2.weight, self.norm2.bias, wr, br64, wo, bo)
+        return ops.SegHeadFn.apply(m, f, self.norm2.weight, self.norm2.bias, wr, br64, wo, None, bo)
 
 
 class Head(nn.Module):
@@ -564,4 +567,8 @@ class Head(nn.Module):
         Ch = self.swin.embed_dim // 2
         NC = self.out_conv.weight.shape[0]
         wo = self.out_conv.weight.permute(2, 3, 4, 1, 0).reshape(27, Ch, NC).contiguous()
-        return ops.SegHeadFn.apply(m, f, self.swin.norm2.weight, self.swin.norm2.bias, wr, br64, wo, self.out_conv.bias)
+        wok = None
+        if ops.N.get_gemm_mode() == 1:
+            wok = self.out_conv.weight.detach().permute(2, 3, 4, 0, 1).reshape(27, NC, Ch).contiguous()
+        return ops.SegHeadFn.apply(m, f, self.swin.norm2.weight, self.swin.norm2.bias, wr, br64, wo, wok,
+                                   self.out_conv.bias)

@@ -226,6 +226,21 @@ def window_attn_bwd(qkv: Tensor, o: Tensor, do: Tensor, lse: Tensor, C: int, hea
     return dqkv
 
 
+def conv3_fwd(x0: Tensor, x1: Optional[Tensor], wt: Tensor, wk: Optional[Tensor], bias: Tensor, out: Tensor, B, dims,
+              Co: int, ncdhw: bool) -> None:
+    """3x3x3 conv forward on a (B, D, H, W) grid: tcgen05 implicit GEMM when the tensor-core mode is on and the
+    geometry is taken (wk = weight as [27][Co][Cin]), else the fp32 CUDA-core kernel (wt = [27][Cin][Co])."""
+    D, H, W = dims
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    if wk is not None and N.get_gemm_mode() == 1:
+        if N.try_call("mic_conv3_tc_fwd", N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(wk), N.ptr(bias), N.ptr(out), B, D, H, W, Co,
+                      int(ncdhw)):
+            return
+    N.call("mic_conv3_fwd", N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(wt), N.ptr(bias), N.ptr(out), B, D, H, W, D, H, W, Co,
+           int(ncdhw))
+
+
 def pad_grid(x: Tensor, dims, pdims) -> Tensor:
     """zero-pad (B,D,H,W,C) -> (B,Dp,Hp,Wp,C)  (F.pad of xa, reference M:350)"""
     B, D, H, W = dims
@@ -365,13 +380,14 @@ class CrossBlockFn(torch.autograd.Function):
     trilinear resampling of xa -> windowed cross attention (q from LN(x), k/v from the resampled xa) -> proj +
     residual -> LN -> MLP -> residual.
 
-    args: x, xa, s1, s2, heads, window, then 19 parameters: norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b},
-    conv_offset.0 weight permuted to (27, 2C, 16) and bias, conv_offset.1.norm.{w,b}, conv_offset.3 weight (3,16),
+    args: x, xa, s1, s2, heads, window, then the parameters: norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b},
+    conv_offset.0 weight permuted to (27, 2C, 16) [and optionally to (27, 16, 2C) for the tcgen05 forward; None
+    otherwise] and bias, conv_offset.1.norm.{w,b}, conv_offset.3 weight (3,16),
     norm2.{w,b}, fc1.{w,b}, fc2.{w,b}."""
 
     @staticmethod
-    def forward(ctx, x, xa, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cb, lnw, lnb, w3, n2w, n2b,
-                f1w, f1b, f2w, f2b):
+    def forward(ctx, x, xa, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cwk, cb, lnw, lnb, w3, n2w,
+                n2b, f1w, f1b, f2w, f2b):
         N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
@@ -383,8 +399,7 @@ class CrossBlockFn(torch.autograd.Function):
         xn_p, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims, pdims)
         xa_p = pad_grid(xa, dims, pdims) if padded else xa
         h16 = _empty((P, HC), x)
-        N.call("mic_conv3_fwd", N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(cw), N.ptr(cb), N.ptr(h16), B, Dp, Hp, Wp, Dp, Hp, Wp,
-               HC, 0)
+        conv3_fwd(xn_p, xa_p, cw, cwk, cb, h16, B, (Dp, Hp, Wp), HC, False)
         pos = _empty((P, 3), x)
         N.call("mic_offset_head_fwd", N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(pos), B, Dp, Hp, Wp, HC, LN_EPS)
         samp = _empty((P, C), x)
@@ -445,7 +460,7 @@ class CrossBlockFn(torch.autograd.Function):
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
         else:
             dxa = dxa_p
-        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, dcb, dlnw, dlnb, dw3,
+        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, None, dcb, dlnw, dlnb, dw3,
                 dn2w, dn2b, df1w, df1b, df2w, df2b)
 
 
@@ -615,7 +630,7 @@ class SegHeadFn(torch.autograd.Function):
     wo: out_conv weight permuted to (27, E/2, NC)."""
 
     @staticmethod
-    def forward(ctx, xm, xf, n2w, n2b, wr, br64, wo, bo):
+    def forward(ctx, xm, xf, n2w, n2b, wr, br64, wo, wok, bo):
         N.check_cuda_f32(xm, xf, n2w, n2b, wr, br64, wo, bo)
         B, D, H, W, E = xm.shape
         T = B * D * H * W
@@ -627,8 +642,7 @@ class SegHeadFn(torch.autograd.Function):
         block_permute(rows, y24, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
         del rows
         logits = _empty((B, NC, 4 * D, 4 * H, 4 * W), xm)
-        N.call("mic_conv3_fwd", N.ptr(y24), Ch, None, 0, N.ptr(wo), N.ptr(bo), N.ptr(logits), B, 4 * D, 4 * H, 4 * W, 4 * D,
-               4 * H, 4 * W, NC, 1)
+        conv3_fwd(y24, None, wo, wok, bo, logits, B, (4 * D, 4 * H, 4 * W), NC, True)
         ctx.save_for_backward(xm, xf, n2w, mean, rstd, xn, wr, y24, wo)
         ctx.meta = (B, D, H, W, E, Ch, NC)
         return logits
@@ -652,7 +666,7 @@ class SegHeadFn(torch.autograd.Function):
         dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
         dwr, dbr64 = linear_bwd_weight(drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
         dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W))
-        return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, dbo
+        return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, None, dbo
 
 
 class DiceBceLossFn(torch.autograd.Function):
