@@ -32,6 +32,9 @@ int tc_linear_bwd_data(const float*, int, const float*, int, int, float*, int, i
                        const float*, int, int, int, cudaStream_t);
 int tc_linear_bwd_weight(const float*, int, const float*, int, float*, int, int, float*, int, int, int, const float*, int, int,
                          cudaStream_t);
+// window_attn_tc.cu (tcgen05; large windows, head_dim 32)
+int tc_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int, int,
+                       int, int, int, float, cudaStream_t);
 // window_attn.cu
 int simt_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int,
                          int, int, int, int, float, cudaStream_t);
@@ -101,6 +104,11 @@ extern "C" int mic_window_attn_fwd(const float* q, int ldq, const float* k, cons
                                    float* lse, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh, int ww,
                                    float scale, void* stream) {
     MIC_REQUIRE(q && k && v && out && lse, "window_attn_fwd: null pointer");
+    if (g_gemm_mode.load() == 1) {
+        int rc = tc_window_attn_fwd(q, ldq, k, v, ldkv, out, ldo, lse, B, Dp, Hp, Wp, heads, hd, wd, wh, ww, scale,
+                                    (cudaStream_t)stream);
+        if (rc != MIC_ERR_UNSUPPORTED) return rc;
+    }
     return simt_window_attn_fwd(q, ldq, k, v, ldkv, out, ldo, lse, B, Dp, Hp, Wp, heads, hd, wd, wh, ww, scale,
                                 (cudaStream_t)stream);
 }
