@@ -17,6 +17,7 @@
 // One MMA consumes 8 reduction elements (32 B of fp32 read as tf32): K-major advances the descriptor start
 // address by 32 B inside the swizzle atom, MN-major by 1024 B.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mic {
@@ -39,6 +40,9 @@ struct TcEpi {
     int kb_total, kb_per_split;
     int round_rn;                           // 1: operands rounded to nearest TF32 in shared memory before the MMA
                                             // (the tensor core itself truncates; truncation is biased toward zero)
+    int split3;                             // 1: 3xTF32 -- x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi);
+                                            // D = Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32-faithful, ~2^-21).  Implies round_rn
+    int nst;                                // pipeline stages in use (3, or 2 when split3 doubles the tiles)
 };
 
 // optional per-CTA phase trace (debug): 16 x u64 globaltimer stamps per CTA when a buffer is registered
@@ -141,9 +145,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int b_groups = (BNT + 31) / 32;
     const int B_BYTES = (B_MN ? b_groups * 32 : BNT) * TKB * 4;
     const int B_STRIDE = 128 * TKB * 4;                       // fixed slot size (16 KB) keeps every slot 1024-aligned
+    const int NST = e.nst;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STRIDE);
+    // split3 (NST == 2): the third stage slot of each operand plus a 4th pair holds the "lo" tiles:
+    //   [A0 A1 A2 | B0 B1 B2 | Alo0 Alo1 | Blo0 Blo1]  (16 KB slots)
+    uint8_t* sAlo = smem + 2 * STAGES * A_BYTES;
+    uint8_t* sBlo = sAlo + 2 * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (e.split3 ? 10 : 6) * A_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -177,8 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             const uint32_t tx = A_BYTES + B_BYTES;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], tx);
                 const int r0 = (kb0 + kb) * TKB;
@@ -205,8 +214,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(e.round_rn ? &conv[s] : &full[s], ph);
                 tc_fence_after();
                 if (kb == 0) trace(4);
@@ -218,6 +227,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
                     const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    if (e.split3) {
+                        const uint32_t al = smem_u32(sAlo + s * A_BYTES), bl = smem_u32(sBlo + s * B_STRIDE);
+                        const uint64_t adl = A_MN ? make_desc(al + k * 1024, 4096, 512, 1) : make_desc(al + k * 32, 16, 1024, 2);
+                        const uint64_t bdl = B_MN ? make_desc(bl + k * 1024, 4096, 512, 1) : make_desc(bl + k * 32, 16, 1024, 2);
+                        umma_tf32(tmem_base, adl, bd, idesc, 1u);
+                        umma_tf32(tmem_base, ad, bdl, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty[s]);          // frees the smem slot once these MMAs retire
             }
@@ -234,11 +250,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int et = (warp - 2) * 32 + lane;                       // 0..127
             const int b_vec = B_BYTES / 16;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(&full[s], ph);
                 float4* a4 = reinterpret_cast<float4*>(sA + s * A_BYTES);
                 float4* b4 = reinterpret_cast<float4*>(sB + s * B_STRIDE);
+                if (e.split3) {
+                    float4* al4 = reinterpret_cast<float4*>(sAlo + s * A_BYTES);
+                    float4* bl4 = reinterpret_cast<float4*>(sBlo + s * B_STRIDE);
+                    auto split = [](float x, float& hi, float& lo) {
+                        hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+                        lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+                    };
+#pragma unroll 4
+                    for (int i = et; i < A_BYTES / 16; i += 128) {
+                        const float4 t = a4[i];
+                        float4 h, l;
+                        split(t.x, h.x, l.x); split(t.y, h.y, l.y); split(t.z, h.z, l.z); split(t.w, h.w, l.w);
+                        a4[i] = h; al4[i] = l;
+                    }
+                    for (int i = et; i < b_vec; i += 128) {
+                        const float4 t = b4[i];
+                        float4 h, l;
+                        split(t.x, h.x, l.x); split(t.y, h.y, l.y); split(t.z, h.z, l.z); split(t.w, h.w, l.w);
+                        b4[i] = h; bl4[i] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
+                    continue;
+                }
 #pragma unroll 4
                 for (int i = et; i < A_BYTES / 16; i += 128) {
                     float4 t = a4[i];
@@ -443,16 +484,19 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
     if (ok && epi == 1 && e.pre) ok = make_map(&mP, e.pre, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldpre, 32, TM, false);
     else mP = mC;
     if (!ok) return MIC_ERR_UNSUPPORTED;
+    e.nst = e.split3 ? 2 : STAGES;
+    if (e.split3) e.round_rn = 1;
     e.kb_total = (R + TKB - 1) / TKB;
     e.kb_per_split = (kb_per_split > 0 && kb_per_split < e.kb_total) ? kb_per_split : e.kb_total;
     const int splits = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
-    const size_t smem = 1024 + (size_t)STAGES * (TM * TKB * 4 + 128 * TKB * 4) + 256;
+    const size_t smem = 1024 + (size_t)(e.split3 ? 10 : 6) * (TM * TKB * 4) + 256;
     dim3 grid((I + TM - 1) / TM, (J + BNT - 1) / BNT, splits);
 #define LAUNCH(AM, BM_, EP)                                                                                      \
     do {                                                                                                         \
         static bool attr_done = false;                                                                           \
         if (!attr_done) {                                                                                        \
-            cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                 (int)(1024 + 10 * TM * TKB * 4 + 256));                                         \
             attr_done = true;                                                                                    \
         }                                                                                                        \
         gemm_tc_kernel<AM, BM_, EP><<<grid, TC_THREADS, smem, st>>>(mA, mB, mC, mP, e, BNT, TCOLS);                       \
@@ -492,7 +536,12 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
     TcEpi e{};
     e.C = Y; e.ldc = ldy; e.I = M; e.J = N; e.bias = bias; e.act = act; e.pre = pre; e.ldpre = ldpre; e.res = res;
     e.ldres = ldres; e.rowscale_i = rowscale; e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
-    e.round_rn = 1;       // forward GEMMs carry the logits parity bar: unbiased TF32 rounding
+    // forward GEMMs carry the logits parity bar (1e-3 vs the fp32 CPU path): 3xTF32 split keeps them fp32-faithful
+    // (the MMAs are not the bottleneck of these HBM/latency-bound shapes); MICFORMER_TF32_FWD=1 selects single-pass
+    // nearest-rounded TF32 (measured 8e-4..1e-3 logits error at 64^3/128^3)
+    static const int fwd_single = []() { const char* v = getenv("MICFORMER_TF32_FWD"); return v && v[0] == '1'; }();
+    e.round_rn = 1;
+    e.split3 = fwd_single ? 0 : 1;
     TcOperand A{X, false, ldx};
     TcOperand B{W, w_is_kn != 0, ldw};      // W[n,k]: K-major; W[k,n]: MN-major
     return tc_gemm(A, B, e, K, 0, st);

@@ -637,12 +637,20 @@ class SegHeadFn(torch.autograd.Function):
         Ch = wo.shape[1]
         NC = wo.shape[2]
         xn, mean, rstd = ln_fwd(xm, xf, n2w, n2b, (B, D, H, W))
+        _dbg = _os.environ.get("MICFORMER_DEBUG_EXACT_TAIL", "")
+        _mode = N.get_gemm_mode()
+        if "gemm" in _dbg:
+            N.set_gemm_mode(0)
         rows = linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True)
+        N.set_gemm_mode(_mode)
         y24 = _empty((B, 4 * D, 4 * H, 4 * W, Ch), xm)
         block_permute(rows, y24, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
         del rows
         logits = _empty((B, NC, 4 * D, 4 * H, 4 * W), xm)
+        if "conv" in _dbg:
+            N.set_gemm_mode(0)
         conv3_fwd(y24, None, wo, wok, bo, logits, B, (4 * D, 4 * H, 4 * W), NC, True)
+        N.set_gemm_mode(_mode)
         ctx.save_for_backward(xm, xf, n2w, mean, rstd, xn, wr, y24, wo)
         ctx.meta = (B, D, H, W, E, Ch, NC)
         return logits
