@@ -25,7 +25,8 @@ namespace mic {
 constexpr int TM = 128;          // output rows per CTA (UMMA M)
 constexpr int TKB = 32;          // reduction elements per stage (128 B of fp32)
 constexpr int STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (+ converters), warps 6-9 converters
+constexpr int NCONV = 256;             // converter threads (warps 2..9)
 
 struct TcEpi {
     float* C; int64_t ldc;
@@ -148,11 +149,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int NST = e.nst;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    // split3 (NST == 2): the third stage slot of each operand plus a 4th pair holds the "lo" tiles:
-    //   [A0 A1 A2 | B0 B1 B2 | Alo0 Alo1 | Blo0 Blo1]  (16 KB slots)
+    // split3 keeps the "lo" tiles in a second set of slots:  [A0 A1 A2 | B0 B1 B2 | Alo0..2 | Blo0..2]  (16 KB each)
     uint8_t* sAlo = smem + 2 * STAGES * A_BYTES;
-    uint8_t* sBlo = sAlo + 2 * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (e.split3 ? 10 : 6) * A_BYTES);
+    uint8_t* sBlo = sAlo + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (e.split3 ? 12 : 6) * A_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -166,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (threadIdx.x == 0) trace(0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], NCONV / 32); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -247,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (e.round_rn) {
             // converter role during the main loop: round the freshly landed A/B tiles to nearest-even TF32 in
             // place (element-wise, so the swizzle is irrelevant), then hand the stage to the MMA warp
-            const int et = (warp - 2) * 32 + lane;                       // 0..127
+            const int et = (warp - 2) * 32 + lane;                       // 0..NCONV-1
             const int b_vec = B_BYTES / 16;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NST;
@@ -263,13 +263,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
                     };
 #pragma unroll 4
-                    for (int i = et; i < A_BYTES / 16; i += 128) {
+                    for (int i = et; i < A_BYTES / 16; i += NCONV) {
                         const float4 t = a4[i];
                         float4 h, l;
                         split(t.x, h.x, l.x); split(t.y, h.y, l.y); split(t.z, h.z, l.z); split(t.w, h.w, l.w);
                         a4[i] = h; al4[i] = l;
                     }
-                    for (int i = et; i < b_vec; i += 128) {
+                    for (int i = et; i < b_vec; i += NCONV) {
                         const float4 t = b4[i];
                         float4 h, l;
                         split(t.x, h.x, l.x); split(t.y, h.y, l.y); split(t.z, h.z, l.z); split(t.w, h.w, l.w);
@@ -281,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     continue;
                 }
 #pragma unroll 4
-                for (int i = et; i < A_BYTES / 16; i += 128) {
+                for (int i = et; i < A_BYTES / 16; i += NCONV) {
                     float4 t = a4[i];
                     uint32_t r0, r1, r2, r3;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(t.x));
@@ -290,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(t.w));
                     a4[i] = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
                 }
-                for (int i = et; i < b_vec; i += 128) {
+                for (int i = et; i < b_vec; i += NCONV) {
                     float4 t = b4[i];
                     uint32_t r0, r1, r2, r3;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(t.x));
@@ -304,6 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
             }
         }
+        if (warp >= 6) goto teardown;           // converter-only warps
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
@@ -397,6 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+teardown:
     if (warp == 2 && lane == 0) trace(7);
     tc_fence_before();
     __syncthreads();
@@ -484,19 +486,19 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
     if (ok && epi == 1 && e.pre) ok = make_map(&mP, e.pre, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldpre, 32, TM, false);
     else mP = mC;
     if (!ok) return MIC_ERR_UNSUPPORTED;
-    e.nst = e.split3 ? 2 : STAGES;
+    e.nst = STAGES;
     if (e.split3) e.round_rn = 1;
     e.kb_total = (R + TKB - 1) / TKB;
     e.kb_per_split = (kb_per_split > 0 && kb_per_split < e.kb_total) ? kb_per_split : e.kb_total;
     const int splits = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
-    const size_t smem = 1024 + (size_t)(e.split3 ? 10 : 6) * (TM * TKB * 4) + 256;
+    const size_t smem = 1024 + (size_t)(e.split3 ? 12 : 6) * (TM * TKB * 4) + 256;
     dim3 grid((I + TM - 1) / TM, (J + BNT - 1) / BNT, splits);
 #define LAUNCH(AM, BM_, EP)                                                                                      \
     do {                                                                                                         \
         static bool attr_done = false;                                                                           \
         if (!attr_done) {                                                                                        \
             cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                 (int)(1024 + 10 * TM * TKB * 4 + 256));                                         \
+                                 (int)(1024 + 12 * TM * TKB * 4 + 256));                                         \
             attr_done = true;                                                                                    \
         }                                                                                                        \
         gemm_tc_kernel<AM, BM_, EP><<<grid, TC_THREADS, smem, st>>>(mA, mB, mC, mP, e, BNT, TCOLS);                       \
