@@ -169,6 +169,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     _native.set_gemm_mode(args.gemm_mode)
 
@@ -344,7 +346,14 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly: drain, rendezvous once
+        # more and leave without running destructors (every rank exits 0; rank 0 has already printed its line)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

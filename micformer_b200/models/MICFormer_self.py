@@ -50,6 +50,9 @@ class DropPath(nn.Module):
 import os as _os
 
 _TWO_STREAMS = _os.environ.get("MICFORMER_TWO_STREAMS", "1") != "0"
+if _TWO_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    # shared modules (patch_embed, samplers, norm) run on both branch streams by design
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 _SIDE = {}
 
 
