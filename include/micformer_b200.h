@@ -136,6 +136,17 @@ int mic_dice_bce_finalize(const double* sums, float* loss, float* coef /*[C*3]*/
 int mic_dice_bce_bwd(const float* logits, const float* target, const float* coef, const float* dloss, float* dlogits,
                      int B, int C, int64_t S, double n_per_channel, void* stream);
 
+/* ---- Multi-tensor Adam (torch.optim.Adam(lr, betas, eps, weight_decay), train_mmwhs_noPad.py:114,201) over all
+ *      parameter tensors in one launch.  params/grads/exp_avg/exp_avg_sq: device arrays of n_tensors pointers (a null
+ *      grad skips the tensor); sizes: device int64[n_tensors]; chunk_tensor/chunk_index: device int[n_chunks] mapping
+ *      each CTA to (tensor, chunk of mic_adam_chunk_elems() elements); steps: device float[n_tensors] (one counter
+ *      per parameter, incremented on the device for tensors that have a gradient); lr: device float scalar
+ *      (CUDA-graph capturable). */
+int mic_adam_chunk_elems(void);
+int mic_adam_step(void* params, void* grads, void* exp_avg, void* exp_avg_sq, const int64_t* sizes,
+                  const int* chunk_tensor, const int* chunk_index, int n_chunks, int n_tensors, float* steps,
+                  const float* lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* ---- small utilities: y = a + rowscale*b with crop from a padded grid (residual after window_reverse + crop
  *      :397-400,:419), fill, axpy ---- */
 int mic_crop_residual(const float* res, const float* branch, const float* rowscale, float* y, int B, int D, int H,

@@ -42,6 +42,8 @@ SIGNATURES = {
     "mic_dice_bce_partial": [P, P, P, I, I, L, P],
     "mic_dice_bce_finalize": [P, P, P, I, D, P],
     "mic_dice_bce_bwd": [P, P, P, P, P, I, I, L, D, P],
+    "mic_adam_chunk_elems": [],
+    "mic_adam_step": [P, P, P, P, P, P, P, I, I, P, P, F, F, F, F, P],
     "mic_crop_residual": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "mic_crop_residual_bwd": [P, P, P, I, I, I, I, I, I, I, I, P],
 }
