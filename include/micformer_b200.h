@@ -101,6 +101,14 @@ int mic_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
  * MIC_ERR_UNSUPPORTED is returned and the caller uses mic_conv3_fwd. */
 int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias, float* y,
                      int B, int D, int H, int W, int Co, int out_ncdhw, void* stream);
+/* tcgen05 backward-data of the same convolution: the forward kernel run on dy with mirrored taps, N tile 32 over the
+ * C0+C1 input channels.  Same arguments as mic_conv3_bwd_data on an unpadded grid; Co in {8,16}, same geometry rule. */
+int mic_conv3_tc_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1, int acc1,
+                          int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream);
+/* Tensor-core backward-weight (warp-level mma.sync m16n8k8 TF32; the reduction runs over positions, so the 27 taps
+ * are index-shifted shared-memory fragment loads): same result as mic_conv3_bwd_weight on an unpadded grid, Co in {8,16}. */
+int mic_conv3_mma_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
+                             int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream);
 
 /* ---- Offset head: LayerNormProxy(16) -> GELU -> Conv3d(16->3,k1,no bias) -> + reference points
  *      (:315-317, :326-337, :360-364).  h (P,HC) -> pos (P,3) with P = B*Dp*Hp*Wp. */

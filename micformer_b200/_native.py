@@ -33,7 +33,9 @@ SIGNATURES = {
     "mic_conv3_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
     "mic_conv3_bwd_data": [P, P, P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "mic_conv3_tc_bwd_data": [P, P, P, I, I, P, I, I, I, I, I, I, I, I, P],
     "mic_conv3_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
+    "mic_conv3_mma_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, P],
     "mic_offset_head_fwd": [P, P, P, P, P, I, I, I, I, I, F, P],
     "mic_offset_head_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, P],
     "mic_deform_sample_fwd": [P, P, P, I, I, I, I, I, I, I, I, P],
@@ -111,10 +113,11 @@ COST = {
                                                                    (1 + (a[10] is not None)))),
     "mic_linear_bwd_weight": lambda a: (2 * a[8] * a[9] * a[10], 4 * (a[8] * a[9] + a[8] * a[10] + a[9] * a[10])),
     "mic_conv3_fwd": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[1] + a[3], a[14]),
-    "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
     "mic_conv3_tc_fwd": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[8], a[9], a[10], a[1] + a[3], a[11]),
     "mic_conv3_bwd_data": lambda a: _cost_conv3(a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[3] + a[6], a[15]),
+    "mic_conv3_tc_bwd_data": lambda a: _cost_conv3(a[8], a[9], a[10], a[11], a[9], a[10], a[11], a[3] + a[6], a[12]),
     "mic_conv3_bwd_weight": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[2] + a[4], a[14]),
+    "mic_conv3_mma_bwd_weight": lambda a: _cost_conv3(a[7], a[8], a[9], a[10], a[8], a[9], a[10], a[2] + a[4], a[11]),
     "mic_window_attn_fwd": lambda a: (4 * _prod(*a[8:12]) * a[12] * a[13] * _prod(*a[14:17]),
                                       4 * (4 * _prod(*a[8:12]) * a[12] * a[13] + _prod(*a[8:12]) * a[12])),
     "mic_window_attn_bwd": lambda a: (10 * _prod(*a[14:18]) * a[18] * a[19] * _prod(*a[20:23]),
@@ -139,10 +142,11 @@ TAG = {
     "mic_linear_bwd_data": lambda a: f"M{a[7]}xN{a[8]}xK{a[9]}",
     "mic_linear_bwd_weight": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",
     "mic_conv3_fwd": lambda a: f"Cin{a[1] + a[3]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
-    "mic_conv3_tc_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, P],
     "mic_conv3_tc_fwd": lambda a: f"Cin{a[1] + a[3]}xCo{a[11]}@{a[7] * a[8] * a[9] * a[10]}",
     "mic_conv3_bwd_data": lambda a: f"Cin{a[3] + a[6]}xCo{a[15]}@{a[8] * a[12] * a[13] * a[14]}",
+    "mic_conv3_tc_bwd_data": lambda a: f"Cin{a[3] + a[6]}xCo{a[12]}@{a[8] * a[9] * a[10] * a[11]}",
     "mic_conv3_bwd_weight": lambda a: f"Cin{a[2] + a[4]}xCo{a[14]}@{a[7] * a[11] * a[12] * a[13]}",
+    "mic_conv3_mma_bwd_weight": lambda a: f"Cin{a[2] + a[4]}xCo{a[11]}@{a[7] * a[8] * a[9] * a[10]}",
 }
 
 
@@ -177,8 +181,7 @@ def profile_end() -> dict:
     return out
 
 
-def call(name: str, *args):
-    """Invoke an ``int``-returning entry point on the current CUDA stream; raise on a non-zero code."""
+def _invoke(name: str, args, allow_unsupported: bool) -> bool:
     lib = load()
     if _prof is not None:
         # the device is drained first so the event pair brackets only this launch (not host queueing gaps);
@@ -188,31 +191,32 @@ def call(name: str, *args):
         e0.record()
         rc = getattr(lib, name)(*args, stream_ptr())
         e1.record()
-        tg = TAG.get(name)
-        key = f"{name}[{tg(args)}]" if tg is not None else name
-        rec = _prof.setdefault(key, {"ev": [], "flops": 0, "bytes": 0})
-        rec["ev"].append((e0, e1))
-        fn = COST.get(name)
-        if fn is not None:
-            f, b = fn(args)
-            rec["flops"] += f; rec["bytes"] += b
+        if rc == 0:
+            tg = TAG.get(name)
+            key = f"{name}[{tg(args)}]" if tg is not None else name
+            rec = _prof.setdefault(key, {"ev": [], "flops": 0, "bytes": 0})
+            rec["ev"].append((e0, e1))
+            fn = COST.get(name)
+            if fn is not None:
+                f, b = fn(args)
+                rec["flops"] += f; rec["bytes"] += b
     else:
         rc = getattr(lib, name)(*args, stream_ptr())
+    if rc == -2 and allow_unsupported:
+        return False
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    return True
+
+
+def call(name: str, *args):
+    """Invoke an ``int``-returning entry point on the current CUDA stream; raise on a non-zero code."""
+    _invoke(name, args, False)
 
 
 def try_call(name: str, *args) -> bool:
     """Like ``call`` but returns False when the entry point declines the shape (MIC_ERR_UNSUPPORTED)."""
-    lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
-    if rc == -2:
-        return False
-    if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
-    if _prof is not None:
-        pass
-    return True
+    return _invoke(name, args, True)
 
 
 def check_cuda_f32(*tensors):

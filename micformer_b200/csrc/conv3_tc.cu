@@ -1,6 +1,8 @@
-// tcgen05 implicit-GEMM 3x3x3 convolution (stride 1, zero pad 1) on channels-last token grids -- forward.
+// tcgen05 implicit-GEMM 3x3x3 convolution (stride 1, zero pad 1) on channels-last token grids -- forward and
+// backward-data (the same kernel: backward-data is the forward conv of dy with the taps mirrored and the roles of
+// the two channel axes swapped, so Wt[tap][ci][co] is read as the [tap][n][k] operand with tap -> 26 - tap).
 //
-//   y[p, o] = bias[o] + sum_{tap} sum_{c} x[p + tap, c] * Wk[tap][o][c]        (M = positions, N = 16, K = 27 * Cin)
+//   y[p, n] = bias[n] + sum_{tap} sum_{c} x[p + tap, c] * Wsrc[tap'][n][c]     (M = positions, N tile = 16 | 32, K = 27 * Cin)
 //
 // No im2col and no per-tap re-fetch: a CTA owns an (8 x 16) x/y footprint and marches over a z segment.  Each
 // input z-plane of the footprint (+1 halo: 10 x 18 positions) is staged ONCE per 16-channel chunk into a 4-slot
@@ -19,15 +21,20 @@ namespace mic {
 constexpr int TX = 8, TY = 16;                 // footprint (x, y) -> 128 output positions per plane (UMMA M)
 constexpr int HXS = TX + 2, HYS = TY + 2;      // haloed plane
 constexpr int PPOS = HXS * HYS;                // 180 positions per staged plane
-constexpr int CCH = 16;                        // channels per chunk
-constexpr int KJ = CCH / 4;                    // 4-channel groups per chunk
-constexpr int PLANE_BYTES = KJ * PPOS * 16;    // 11520
 constexpr int RING = 4;
-constexpr int W_BYTES = 27 * KJ * 16 * 16;     // 27648: [tap][kj][o=16][4 floats]
 constexpr int CT_THREADS = 160;
+// template parameters of the kernel: KJ = 4-channel groups per K chunk (chunk = 4*KJ input channels: 16, or 8 for the
+// 8-channel dy of out_conv's backward), NT = output channels per CTA (UMMA N).
+//   plane slot  : KJ * PPOS * 16 bytes            [kj][pos][4 floats]
+//   weight chunk: 27 * KJ * NT * 16 bytes         [tap][kj][n][4 floats]
 
 struct ConvTcGeom {
-    int B, D, H, W, C0, C1, Co, Dz, nseg, nfy, nfx;
+    int B, D, H, W;
+    int C0, C1;            // input channels: x0 | x1 (channels-last), or C0 planes of an NCDHW tensor (in_ncdhw)
+    int N0, N1;            // output channels: y0 | y1 (channels-last), or N0 planes of an NCDHW tensor (out_ncdhw)
+    int acc0, acc1;        // accumulate into y0 / y1 instead of storing
+    int in_ncdhw, out_ncdhw, flip;
+    int Dz, nseg, nfy, nfx, nwb;
 };
 
 __device__ __forceinline__ uint32_t csmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,13 +81,17 @@ __device__ __forceinline__ float rna_tf32(float x) {
 }
 __device__ __forceinline__ float4 rna4(float4 v) { return make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w)); }
 
+template <int KJ, int NT>
 __global__ void __launch_bounds__(CT_THREADS, 2)
-conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ Wk,
-                    const float* __restrict__ bias, float* __restrict__ y, ConvTcGeom g, int out_ncdhw, int tcols) {
+conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ Wsrc,
+                const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, ConvTcGeom g, int tcols) {
+    constexpr int CCH = 4 * KJ;
+    constexpr int PLANE_BYTES = KJ * PPOS * 16;
+    constexpr int W_BYTES = 27 * KJ * NT * 16;
     extern __shared__ __align__(128) uint8_t csm[];
     uint8_t* ring = csm;                                   // RING planes
-    uint8_t* wbuf = csm + RING * PLANE_BYTES;              // 2 weight buffers
-    uint64_t* pfull = reinterpret_cast<uint64_t*>(wbuf + 2 * W_BYTES);
+    uint8_t* wbuf = csm + RING * PLANE_BYTES;              // nwb weight buffers
+    uint64_t* pfull = reinterpret_cast<uint64_t*>(wbuf + g.nwb * W_BYTES);
     uint64_t* pempty = pfull + RING;
     uint64_t* wfull = pempty + RING;
     uint64_t* wempty = wfull + 2;
@@ -89,7 +100,10 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Cin = g.C0 + g.C1;
+    const int Ntot = g.N0 + g.N1;
+    const int n0 = blockIdx.y * NT;                        // first output channel of this CTA
     const int nchunks = (Cin + CCH - 1) / CCH;
+    const int nwb = g.nwb;
     // tile decode: blockIdx.x = ((b*nseg + seg)*nfy + fy)*nfx + fx
     int t = blockIdx.x;
     const int fx = t % g.nfx; t /= g.nfx;
@@ -99,6 +113,7 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
     const int xb = fx * TX, yb = fy * TY, zs = seg * g.Dz;
     const int nz = min(g.Dz, g.D - zs);                    // output planes of this segment
     const int planes_per_chunk = nz + 2;
+    const int64_t S = (int64_t)g.D * g.H * g.W;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RING; ++s) { cbar_init(&pfull[s], 128); cbar_init(&pempty[s], 1); }
@@ -119,8 +134,8 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
         // ------------------------------------------------------------------ producers
         const int tid = threadIdx.x;     // 0..127
         int n = 0;                       // running plane counter (ring position)
-        constexpr int PL = (PPOS * KJ + 127) / 128;          // float4 gathers per thread per plane (6)
-        constexpr int WL = (27 * 16 * KJ + 127) / 128;       // float4 loads per thread per weight chunk (14)
+        constexpr int PL = (PPOS * KJ + 127) / 128;          // float4 gathers per thread per plane
+        constexpr int WL = (27 * NT * KJ + 127) / 128;       // float4 loads per thread per weight chunk
         // gather one haloed plane chunk into registers (all loads in flight before the first use)
         auto gather = [&](int z, int c0, float4 (&r)[PL]) {
             const bool zok = z >= 0 && z < g.D;
@@ -132,9 +147,17 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
                 const int c = c0 + kj * 4;
                 r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (idx < PPOS * KJ && zok && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W && c < Cin) {
-                    const int64_t row = (((int64_t)b * g.D + z) * g.H + yy) * g.W + xx;
-                    r[i] = c < g.C0 ? *reinterpret_cast<const float4*>(x0 + row * g.C0 + c)
-                                    : *reinterpret_cast<const float4*>(x1 + row * g.C1 + (c - g.C0));
+                    if (g.in_ncdhw) {
+                        const float* src = x0 + ((int64_t)b * Cin + c) * S + ((int64_t)z * g.H + yy) * g.W + xx;
+                        r[i].x = src[0];
+                        if (c + 1 < Cin) r[i].y = src[S];
+                        if (c + 2 < Cin) r[i].z = src[2 * S];
+                        if (c + 3 < Cin) r[i].w = src[3 * S];
+                    } else {
+                        const int64_t row = (((int64_t)b * g.D + z) * g.H + yy) * g.W + xx;
+                        r[i] = c < g.C0 ? *reinterpret_cast<const float4*>(x0 + row * g.C0 + c)
+                                        : *reinterpret_cast<const float4*>(x1 + row * g.C1 + (c - g.C0));
+                    }
                 }
             }
         };
@@ -142,26 +165,35 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
         gather(zs - 1, 0, cur);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int c0 = ch * CCH;
-            // weights of this chunk: [tap][kj][o][4]
+            // weights of this chunk: smem [tap][kj][n][4] <- Wsrc[tap'][n0 + n][c0 + 4 kj ..]
             {
-                const int wb = ch & 1;
+                const int wb = ch % nwb;
                 float4 wr[WL];
 #pragma unroll
                 for (int i = 0; i < WL; ++i) {
                     const int idx = tid + i * 128;
-                    const int kj = idx % KJ, o = (idx / KJ) % 16, tap = idx / (KJ * 16);
+                    const int kj = idx % KJ, o = (idx / KJ) % NT, tap = idx / (KJ * NT);
                     const int c = c0 + kj * 4;
                     wr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < 27 * 16 * KJ && o < g.Co && c < Cin)
-                        wr[i] = *reinterpret_cast<const float4*>(Wk + ((int64_t)tap * g.Co + o) * Cin + c);
+                    if (idx < 27 * NT * KJ && n0 + o < Ntot && c < Cin) {
+                        const int ts = g.flip ? 26 - tap : tap;
+                        const float* src = Wsrc + ((int64_t)ts * Ntot + n0 + o) * Cin + c;
+                        if ((Cin & 3) == 0) wr[i] = *reinterpret_cast<const float4*>(src);
+                        else {
+                            wr[i].x = src[0];
+                            if (c + 1 < Cin) wr[i].y = src[1];
+                            if (c + 2 < Cin) wr[i].z = src[2];
+                            if (c + 3 < Cin) wr[i].w = src[3];
+                        }
+                    }
                 }
-                cbar_wait(&wempty[wb], ((ch >> 1) & 1) ^ 1);
+                cbar_wait(&wempty[wb], ((ch / nwb) & 1) ^ 1);
                 float4* wd = reinterpret_cast<float4*>(wbuf + wb * W_BYTES);
 #pragma unroll
                 for (int i = 0; i < WL; ++i) {
                     const int idx = tid + i * 128;
-                    const int kj = idx % KJ, o = (idx / KJ) % 16, tap = idx / (KJ * 16);
-                    if (idx < 27 * 16 * KJ) wd[(tap * KJ + kj) * 16 + o] = rna4(wr[i]);
+                    const int kj = idx % KJ, o = (idx / KJ) % NT, tap = idx / (KJ * NT);
+                    if (idx < 27 * NT * KJ) wd[(tap * KJ + kj) * NT + o] = rna4(wr[i]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 cbar_arrive(&wfull[wb]);
@@ -193,58 +225,73 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
         const int r = q * 32 + lane;                          // row in the 128-position plane tile
         const int yy = yb + r / TX, xx = xb + r % TX;
         const bool ok = yy < g.H && xx < g.W;
-        const int64_t S = (int64_t)g.D * g.H * g.W;
         for (int zi = 0; zi < nz; ++zi) {
-            uint32_t v[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(zi * 16)));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!ok) continue;
             const int z = zs + zi;
             const int64_t sp = ((int64_t)z * g.H + yy) * g.W + xx;
-            if (out_ncdhw) {
-                for (int o = 0; o < g.Co; ++o)
-                    y[((int64_t)b * g.Co + o) * S + sp] = __uint_as_float(v[o]) + (bias ? bias[o] : 0.f);
-            } else {
-                float* dst = y + ((int64_t)b * S + sp) * g.Co;
-                if (g.Co == 16) {
 #pragma unroll
-                    for (int o4 = 0; o4 < 4; ++o4) {
-                        float4 bb = bias ? *reinterpret_cast<const float4*>(bias + o4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4*>(dst + o4 * 4) =
-                            make_float4(__uint_as_float(v[o4 * 4]) + bb.x, __uint_as_float(v[o4 * 4 + 1]) + bb.y,
-                                        __uint_as_float(v[o4 * 4 + 2]) + bb.z, __uint_as_float(v[o4 * 4 + 3]) + bb.w);
+            for (int gi = 0; gi < NT / 16; ++gi) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(zi * NT + gi * 16)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!ok) continue;
+                const int nb = n0 + gi * 16;
+                if (g.out_ncdhw) {
+                    for (int o = 0; o < 16 && nb + o < Ntot; ++o) {
+                        float* dst = y0 + ((int64_t)b * Ntot + nb + o) * S + sp;
+                        float val = __uint_as_float(v[o]) + (bias ? bias[nb + o] : 0.f);
+                        if (g.acc0) val += *dst;
+                        *dst = val;
                     }
                 } else {
-                    for (int o = 0; o < g.Co; ++o) dst[o] = __uint_as_float(v[o]) + (bias ? bias[o] : 0.f);
+#pragma unroll
+                    for (int o4 = 0; o4 < 4; ++o4) {
+                        const int c = nb + o4 * 4;
+                        if (c >= Ntot) continue;
+                        float4 val = make_float4(__uint_as_float(v[o4 * 4]), __uint_as_float(v[o4 * 4 + 1]),
+                                                 __uint_as_float(v[o4 * 4 + 2]), __uint_as_float(v[o4 * 4 + 3]));
+                        if (bias) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias + c);
+                            val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
+                        }
+                        float4* dst;
+                        int accf;
+                        if (c < g.N0) { dst = reinterpret_cast<float4*>(y0 + ((int64_t)b * S + sp) * g.N0 + c); accf = g.acc0; }
+                        else { dst = reinterpret_cast<float4*>(y1 + ((int64_t)b * S + sp) * g.N1 + (c - g.N0)); accf = g.acc1; }
+                        if (accf) {
+                            const float4 old = *dst;
+                            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                        }
+                        *dst = val;
+                    }
                 }
             }
         }
     } else if (lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t ring_addr = csmem_u32(ring), w_addr = csmem_u32(wbuf);
-        int n0 = 0;
-        for (int ch = 0; ch < nchunks; ++ch, n0 += planes_per_chunk) {
-            const int wb = ch & 1;
-            cbar_wait(&wfull[wb], (ch >> 1) & 1);
+        int n0p = 0;
+        for (int ch = 0; ch < nchunks; ++ch, n0p += planes_per_chunk) {
+            const int wb = ch % nwb;
+            cbar_wait(&wfull[wb], (ch / nwb) & 1);
             const int cvalid = min(CCH, Cin - ch * CCH);
             const int ksteps = (cvalid + 7) / 8;                 // K = 8 channels per MMA
-            int waited = n0 - 1;                                  // highest plane index already waited for
+            int waited = n0p - 1;                                 // highest plane index already waited for
             for (int zi = 0; zi < nz; ++zi) {
-                const int need = n0 + zi + 2;                     // planes n0+zi .. n0+zi+2
+                const int need = n0p + zi + 2;                    // planes n0p+zi .. n0p+zi+2
                 while (waited < need) {
                     ++waited;
                     cbar_wait(&pfull[waited % RING], (waited / RING) & 1);
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dcol = tmem + (uint32_t)(zi * 16);
+                const uint32_t dcol = tmem + (uint32_t)(zi * NT);
                 for (int tz = 0; tz < 3; ++tz) {
-                    const uint32_t pbase = ring_addr + (uint32_t)(((n0 + zi + tz) % RING) * PLANE_BYTES);
+                    const uint32_t pbase = ring_addr + (uint32_t)(((n0p + zi + tz) % RING) * PLANE_BYTES);
 #pragma unroll
                     for (int ty = 0; ty < 3; ++ty)
 #pragma unroll
@@ -252,15 +299,15 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
                             const int tap = (tz * 3 + ty) * 3 + tx;
                             for (int ks = 0; ks < ksteps; ++ks) {
                                 const uint64_t ad = cdesc(pbase + (uint32_t)((ty * HXS + tx) * 16 + 2 * ks * PPOS * 16), PPOS * 16, HXS * 16);
-                                const uint64_t bd = cdesc(w_addr + (uint32_t)(wb * W_BYTES + (tap * KJ + 2 * ks) * 256), 256, 128);
+                                const uint64_t bd = cdesc(w_addr + (uint32_t)(wb * W_BYTES + (tap * KJ + 2 * ks) * NT * 16), NT * 16, 128);
                                 cmma(dcol, ad, bd, idesc, (ch | tap | ks) ? 1u : 0u);
                             }
                         }
                 }
-                ccommit(&pempty[(n0 + zi) % RING]);               // plane z-1 is no longer needed
+                ccommit(&pempty[(n0p + zi) % RING]);              // plane z-1 is no longer needed
             }
-            ccommit(&pempty[(n0 + nz) % RING]);                   // the last two planes of this chunk
-            ccommit(&pempty[(n0 + nz + 1) % RING]);
+            ccommit(&pempty[(n0p + nz) % RING]);                  // the last two planes of this chunk
+            ccommit(&pempty[(n0p + nz + 1) % RING]);
             ccommit(&wempty[wb]);
         }
         ccommit(accdone);
@@ -273,33 +320,58 @@ conv3_tc_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
     }
 }
 
+template <int KJ, int NT>
+static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, const float* bias, float* y0, float* y1,
+                          ConvTcGeom g, cudaStream_t st, const char* who) {
+    const int Cin = g.C0 + g.C1, Ntot = g.N0 + g.N1;
+    const int nchunks = (Cin + 4 * KJ - 1) / (4 * KJ);
+    const int nych = (Ntot + NT - 1) / NT;
+    g.nfy = g.H / TY; g.nfx = g.W / TX;
+    g.nwb = nchunks > 1 ? 2 : 1;
+    const int foot = g.B * g.nfy * g.nfx;
+    // z segment length: enough CTAs to fill the GPU; Dz * NT accumulator columns, two CTAs per SM share 512
+    int Dz = 256 / NT;
+    while (Dz > 2 && (int64_t)foot * ((g.D + Dz - 1) / Dz) * nych < 2 * num_sms()) Dz >>= 1;
+    if (Dz > g.D) Dz = g.D;
+    g.Dz = Dz; g.nseg = (g.D + Dz - 1) / Dz;
+    int tcols = 32;
+    while (tcols < Dz * NT) tcols <<= 1;
+    const size_t smem = RING * (KJ * PPOS * 16) + g.nwb * (27 * KJ * NT * 16) + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv3_tc_kernel<KJ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             RING * (KJ * PPOS * 16) + 2 * (27 * KJ * NT * 16) + 256);
+        attr = true;
+    }
+    dim3 grid((unsigned)((int64_t)foot * g.nseg), (unsigned)nych);
+    conv3_tc_kernel<KJ, NT><<<grid, CT_THREADS, smem, st>>>(x0, x1, Wsrc, bias, y0, y1, g, tcols);
+    return check_launch(who);
+}
+
+static bool misaligned16(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15); }
+
 // returns MIC_ERR_UNSUPPORTED when the geometry is not taken (caller falls back to the CUDA-core kernel)
 int tc_conv3_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias, float* y, int B,
                  int D, int H, int W, int Co, int out_ncdhw, cudaStream_t st) {
-    if (W % TX || H % TY || Co > 16 || Co < 1 || (C0 & 3) || (C1 & 3)) return MIC_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(x0) & 15) || (x1 && (reinterpret_cast<uintptr_t>(x1) & 15)) ||
-        (reinterpret_cast<uintptr_t>(Wk) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
-        return MIC_ERR_UNSUPPORTED;
+    if (W % TX || H % TY || Co > 16 || Co < 1 || (C0 & 3) || (C1 & 3) || (!out_ncdhw && (Co & 3))) return MIC_ERR_UNSUPPORTED;
+    if (misaligned16(x0) || misaligned16(x1) || misaligned16(Wk) || misaligned16(y) || misaligned16(bias)) return MIC_ERR_UNSUPPORTED;
     ConvTcGeom g{};
-    g.B = B; g.D = D; g.H = H; g.W = W; g.C0 = C0; g.C1 = C1; g.Co = Co;
-    g.nfy = H / TY; g.nfx = W / TX;
-    const int foot = B * g.nfy * g.nfx;
-    // z segment length: enough CTAs to fill the GPU, at most 16 planes (16 TMEM columns each)
-    int Dz = 16;
-    while (Dz > 2 && (int64_t)foot * ((D + Dz - 1) / Dz) < 2 * num_sms()) Dz >>= 1;
-    if (Dz > D) Dz = D;
-    g.Dz = Dz; g.nseg = (D + Dz - 1) / Dz;
-    int tcols = 32;
-    while (tcols < Dz * 16) tcols <<= 1;
-    const size_t smem = RING * PLANE_BYTES + 2 * W_BYTES + 256;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(conv3_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    const int64_t ctas = (int64_t)foot * g.nseg;
-    conv3_tc_fwd_kernel<<<(unsigned)ctas, CT_THREADS, smem, st>>>(x0, x1, Wk, bias, y, g, out_ncdhw, tcols);
-    return check_launch("conv3_tc_fwd_kernel");
+    g.B = B; g.D = D; g.H = H; g.W = W; g.C0 = C0; g.C1 = C1; g.N0 = Co; g.N1 = 0;
+    g.out_ncdhw = out_ncdhw;
+    return launch_conv_tc<4, 16>(x0, x1, Wk, bias, y, nullptr, g, st, "conv3_tc_kernel<fwd>");
+}
+
+// dx0 | dx1 (channels-last, C0 | C1 channels) (+)= conv3^T(dy; Wt) with Wt = [27][C0 + C1][Co]; dy has Co channels,
+// channels-last or NCDHW
+int tc_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1, int acc1, int B,
+                      int D, int H, int W, int Co, int dy_ncdhw, cudaStream_t st) {
+    if (W % TX || H % TY || (Co != 8 && Co != 16) || (C0 & 3) || (C1 & 3) || C0 + C1 < 16) return MIC_ERR_UNSUPPORTED;
+    if (misaligned16(dy) || misaligned16(Wt) || misaligned16(dx0) || misaligned16(dx1)) return MIC_ERR_UNSUPPORTED;
+    ConvTcGeom g{};
+    g.B = B; g.D = D; g.H = H; g.W = W; g.C0 = Co; g.C1 = 0; g.N0 = C0; g.N1 = C1; g.acc0 = acc0; g.acc1 = acc1;
+    g.in_ncdhw = dy_ncdhw; g.flip = 1;
+    if (Co == 8) return launch_conv_tc<2, 32>(dy, nullptr, Wt, nullptr, dx0, dx1, g, st, "conv3_tc_kernel<bwd_data,8>");
+    return launch_conv_tc<4, 32>(dy, nullptr, Wt, nullptr, dx0, dx1, g, st, "conv3_tc_kernel<bwd_data,16>");
 }
 
 }  // namespace mic
@@ -309,5 +381,13 @@ extern "C" int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1
     MIC_REQUIRE(x0 && Wk && y && (C1 == 0 || x1), "conv3_tc_fwd: null pointer");
     int rc = mic::tc_conv3_fwd(x0, C0, x1, C1, Wk, bias, y, B, D, H, W, Co, out_ncdhw, (cudaStream_t)stream);
     if (rc == MIC_ERR_UNSUPPORTED) return mic::fail(MIC_ERR_UNSUPPORTED, "conv3_tc_fwd: geometry (%d,%d,%d) Co=%d not taken", D, H, W, Co);
+    return rc;
+}
+
+extern "C" int mic_conv3_tc_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1,
+                                     int acc1, int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream) {
+    MIC_REQUIRE(dy && Wt && dx0 && (C1 == 0 || dx1), "conv3_tc_bwd_data: null pointer");
+    int rc = mic::tc_conv3_bwd_data(dy, Wt, dx0, C0, acc0, dx1, C1, acc1, B, D, H, W, Co, dy_ncdhw, (cudaStream_t)stream);
+    if (rc == MIC_ERR_UNSUPPORTED) return mic::fail(MIC_ERR_UNSUPPORTED, "conv3_tc_bwd_data: geometry (%d,%d,%d) Co=%d not taken", D, H, W, Co);
     return rc;
 }

@@ -241,6 +241,35 @@ def conv3_fwd(x0: Tensor, x1: Optional[Tensor], wt: Tensor, wk: Optional[Tensor]
            int(ncdhw))
 
 
+def conv3_bwd_data(dy: Tensor, wt: Tensor, dx0: Tensor, acc0: bool, dx1: Optional[Tensor], acc1: bool, B, dims, Co: int,
+                   dy_ncdhw: bool) -> None:
+    """dx0 | dx1 (+)= transposed 3x3x3 conv of dy with wt = [27][Cin][Co]: tcgen05 implicit GEMM (the forward kernel
+    with mirrored taps) when the tensor-core mode is on and the geometry is taken, else the fp32 CUDA-core kernel."""
+    D, H, W = dims
+    C0 = dx0.shape[-1]
+    C1 = dx1.shape[-1] if dx1 is not None else 0
+    if N.get_gemm_mode() == 1:
+        if N.try_call("mic_conv3_tc_bwd_data", N.ptr(dy), N.ptr(wt), N.ptr(dx0), C0, int(acc0), N.ptr(dx1), C1, int(acc1), B, D,
+                      H, W, Co, int(dy_ncdhw)):
+            return
+    N.call("mic_conv3_bwd_data", N.ptr(dy), N.ptr(wt), N.ptr(dx0), C0, int(acc0), N.ptr(dx1), C1, int(acc1), B, D, H, W, D, H,
+           W, Co, int(dy_ncdhw))
+
+
+def conv3_bwd_weight(dy: Tensor, x0: Tensor, x1: Optional[Tensor], dwt: Tensor, dbias: Optional[Tensor], B, dims, Co: int,
+                     dy_ncdhw: bool) -> None:
+    """dwt[27][Cin][Co] += , dbias[Co] += : TF32 mma.sync kernel in tensor-core mode, else the fp32 CUDA-core kernel."""
+    D, H, W = dims
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    if N.get_gemm_mode() == 1:
+        if N.try_call("mic_conv3_mma_bwd_weight", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(dwt), N.ptr(dbias), B, D, H, W,
+                      Co, int(dy_ncdhw)):
+            return
+    N.call("mic_conv3_bwd_weight", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(dwt), N.ptr(dbias), B, D, H, W, D, H, W, Co,
+           int(dy_ncdhw))
+
+
 def pad_grid(x: Tensor, dims, pdims) -> Tensor:
     """zero-pad (B,D,H,W,C) -> (B,Dp,Hp,Wp,C)  (F.pad of xa, reference M:350)"""
     B, D, H, W = dims
@@ -451,10 +480,8 @@ class CrossBlockFn(torch.autograd.Function):
                    N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
             dcw = _zeros(tuple(cw.shape), x); dcb = _zeros((HC,), x)
             sb.hold(dh16, xn_p, xa_p)
-            sb.run(N.call, "mic_conv3_bwd_weight", N.ptr(dh16), N.ptr(xn_p), C, N.ptr(xa_p), C, N.ptr(dcw), N.ptr(dcb), B, Dp,
-                   Hp, Wp, Dp, Hp, Wp, HC, 0)
-            N.call("mic_conv3_bwd_data", N.ptr(dh16), N.ptr(cw), N.ptr(dxn_p), C, 1, N.ptr(dxa_p), C, 1, B, Dp, Hp, Wp, Dp, Hp,
-                   Wp, HC, 0)
+            sb.run(conv3_bwd_weight, dh16, xn_p, xa_p, dcw, dcb, B, (Dp, Hp, Wp), HC, False)
+            conv3_bwd_data(dh16, cw, dxn_p.view(B, Dp, Hp, Wp, C), True, dxa_p, True, B, (Dp, Hp, Wp), HC, False)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
         if padded:
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
@@ -663,11 +690,9 @@ class SegHeadFn(torch.autograd.Function):
         T = B * D * H * W
         dlog = dlog.contiguous()
         dy24 = torch.empty_like(y24)
-        N.call("mic_conv3_bwd_data", N.ptr(dlog), N.ptr(wo), N.ptr(dy24), Ch, 0, None, 0, 0, B, 4 * D, 4 * H, 4 * W, 4 * D,
-               4 * H, 4 * W, NC, 1)
+        conv3_bwd_data(dlog, wo, dy24, False, None, False, B, (4 * D, 4 * H, 4 * W), NC, True)
         dwo = torch.zeros_like(wo); dbo = _zeros((NC,), xm)
-        N.call("mic_conv3_bwd_weight", N.ptr(dlog), N.ptr(y24), Ch, None, 0, N.ptr(dwo), N.ptr(dbo), B, 4 * D, 4 * H, 4 * W,
-               4 * D, 4 * H, 4 * W, NC, 1)
+        conv3_bwd_weight(dlog, y24, None, dwo, dbo, B, (4 * D, 4 * H, 4 * W), NC, True)
         drows = _empty((T, 64 * Ch), xm)
         block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
         del dy24

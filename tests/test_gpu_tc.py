@@ -150,3 +150,47 @@ def test_tc_w7_model_logits(tc_mode):
     rel = float((y - ref).abs().max() / ref.abs().max())
     print(f"TF32 w7 logits rel err {rel:.2e}")
     assert rel < 1e-3
+
+
+@pytest.mark.parametrize("C0,C1,Co,dims,ncdhw", [(48, 48, 16, (8, 32, 32), False),      # conv_offset, stage-0 planes
+                                                 (96, 96, 16, (16, 16, 16), False),     # conv_offset, stage 1
+                                                 (24, 0, 8, (12, 32, 16), True),        # out_conv (NCDHW logits / dlogits)
+                                                 (32, 0, 16, (5, 16, 8), False)])
+def test_tc_conv3_fwd_bwd(tc_mode, C0, C1, Co, dims, ncdhw):
+    """tcgen05 implicit-GEMM 3x3x3 conv: forward, backward-data (mirrored taps through the same kernel, accumulate
+    epilogue) and backward-weight against F.conv3d autograd in fp64."""
+    from micformer_b200 import _native as N, ops
+    from helpers import rel_err
+    B = 2
+    D, H, W = dims
+    Cin = C0 + C1
+    x0 = _rand(B, D, H, W, C0, seed=1).double().requires_grad_(True)
+    x1 = _rand(B, D, H, W, C1, seed=2).double().requires_grad_(True) if C1 else None
+    w = (_rand(Co, Cin, 3, 3, 3, seed=3) * 0.1).double().requires_grad_(True)
+    b = _rand(Co, seed=4).double().requires_grad_(True)
+    xin = torch.cat([x0, x1], -1) if C1 else x0
+    y_ref = F.conv3d(xin.permute(0, 4, 1, 2, 3), w, b, padding=1)
+    gy = _rand(*y_ref.shape, seed=5).double()
+    (y_ref * gy).sum().backward()
+    wt = w.detach().float().permute(2, 3, 4, 1, 0).reshape(27, Cin, Co).contiguous().to(DEV)
+    wk = w.detach().float().permute(2, 3, 4, 0, 1).reshape(27, Co, Cin).contiguous().to(DEV)
+    x0d = x0.detach().float().to(DEV)
+    x1d = x1.detach().float().to(DEV) if C1 else None
+    y = torch.empty((B, Co, D, H, W) if ncdhw else (B, D, H, W, Co), device=DEV)
+    N.call("mic_conv3_tc_fwd", N.ptr(x0d), C0, N.ptr(x1d), C1, N.ptr(wk), N.ptr(b.detach().float().to(DEV)), N.ptr(y), B, D,
+           H, W, Co, int(ncdhw))
+    yk = y.cpu() if ncdhw else y.cpu().permute(0, 4, 1, 2, 3)
+    assert max_rel(yk, y_ref.detach()) < 2e-3
+    dy = (gy if ncdhw else gy.permute(0, 2, 3, 4, 1)).float().contiguous().to(DEV)
+    dx0 = torch.full((B, D, H, W, C0), 1.0, device=DEV)         # acc0=1: accumulates onto the ones
+    dx1 = torch.full((B, D, H, W, max(C1, 4)), 7.0, device=DEV)  # acc1=0: overwritten
+    N.call("mic_conv3_tc_bwd_data", N.ptr(dy), N.ptr(wt), N.ptr(dx0), C0, 1, N.ptr(dx1) if C1 else None, C1, 0, B, D, H, W,
+           Co, int(ncdhw))
+    assert rel_err(dx0.cpu() - 1.0, x0.grad) < 2e-3
+    if C1:
+        assert rel_err(dx1.cpu(), x1.grad) < 2e-3
+    dwt = torch.zeros_like(wt)
+    dbias = torch.zeros(Co, device=DEV)
+    ops.conv3_bwd_weight(dy, x0d, x1d, dwt, dbias, B, (D, H, W), Co, ncdhw)
+    dw_ref = w.grad.permute(2, 3, 4, 1, 0).reshape(27, Cin, Co)
+    assert rel_err(dwt.cpu(), dw_ref) < 2e-3 and rel_err(dbias.cpu(), b.grad) < 1e-4
