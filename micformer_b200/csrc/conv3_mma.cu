@@ -81,42 +81,68 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
         const int b = (int)t;
         const int z0 = bz * MB_Z, y0 = by * MB_Y, x0c = bx * MB_X;
         __syncthreads();                    // previous brick fully consumed
-        // x halo (zero outside the volume), 32 channels, rounded to TF32
-        for (int idx = tid; idx < M_NH * 8; idx += M_THREADS) {
-            const int hp = idx >> 3, c4 = (idx & 7) * 4;
-            const int hx = hp % MH_X, hy = (hp / MH_X) % MH_Y, hz = hp / (MH_X * MH_Y);
-            const int z = z0 + hz - 1, yy = y0 + hy - 1, x = x0c + hx - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int c = c0 + c4;
-            if (z >= 0 && z < g.D && yy >= 0 && yy < g.H && x >= 0 && x < g.W && c < Cin) {
-                const int64_t row = (((int64_t)b * g.D + z) * g.H + yy) * g.W + x;
-                v = c < g.C0 ? *reinterpret_cast<const float4*>(x0 + row * g.C0 + c)
-                             : *reinterpret_cast<const float4*>(x1 + row * g.C1 + (c - g.C0));
+        // x halo (zero outside the volume), 32 channels, rounded to TF32: all loads of the thread in flight before the
+        // first store
+        {
+            constexpr int XL = (M_NH * 8 + M_THREADS - 1) / M_THREADS;      // 10
+            float4 xv[XL];
+#pragma unroll
+            for (int i = 0; i < XL; ++i) {
+                const int idx = tid + i * M_THREADS;
+                const int hp = idx >> 3, c4 = (idx & 7) * 4;
+                const int hx = hp % MH_X, hy = (hp / MH_X) % MH_Y, hz = hp / (MH_X * MH_Y);
+                const int z = z0 + hz - 1, yy = y0 + hy - 1, x = x0c + hx - 1;
+                xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c = c0 + c4;
+                if (idx < M_NH * 8 && z >= 0 && z < g.D && yy >= 0 && yy < g.H && x >= 0 && x < g.W && c < Cin) {
+                    const int64_t row = (((int64_t)b * g.D + z) * g.H + yy) * g.W + x;
+                    xv[i] = c < g.C0 ? __ldg(reinterpret_cast<const float4*>(x0 + row * g.C0 + c))
+                                     : __ldg(reinterpret_cast<const float4*>(x1 + row * g.C1 + (c - g.C0)));
+                }
             }
-            *reinterpret_cast<float4*>(Xs + hp * XS + c4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+#pragma unroll
+            for (int i = 0; i < XL; ++i) {
+                const int idx = tid + i * M_THREADS;
+                if (idx < M_NH * 8)
+                    *reinterpret_cast<float4*>(Xs + (idx >> 3) * XS + (idx & 7) * 4) =
+                        make_float4(to_tf32(xv[i].x), to_tf32(xv[i].y), to_tf32(xv[i].z), to_tf32(xv[i].w));
+            }
         }
         // dy brick (zero outside), Co padded to COP
-        for (int idx = tid; idx < M_NB * COP; idx += M_THREADS) {
-            int pos, o;
-            if (dy_ncdhw) { pos = idx % M_NB; o = idx / M_NB; } else { o = idx % COP; pos = idx / COP; }
-            const int lx = pos % MB_X, ly = (pos / MB_X) % MB_Y, lz = pos / (MB_X * MB_Y);
-            const int z = z0 + lz, yy = y0 + ly, x = x0c + lx;
-            float v = 0.f;
-            if (o < g.Co && z < g.D && yy < g.H && x < g.W) {
-                const int64_t sp = ((int64_t)z * g.H + yy) * g.W + x;
-                v = dy_ncdhw ? dy[((int64_t)b * g.Co + o) * S + sp] : dy[((int64_t)b * S + sp) * g.Co + o];
-            }
-            dYs[pos * DS + o] = to_tf32(v);
-            if (want_bias) {
-                // lanes of a warp share o (NCDHW: 128 % 32 == 0) or hold o = lane % COP (channels-last)
-                float s = v;
-                if (dy_ncdhw) {
-                    s = warp_sum(s);
-                    if (lane == 0 && o < g.Co) atomicAdd(&bsum[o], s);
-                } else {
+        {
+            constexpr int DL = (M_NB * COP + M_THREADS - 1) / M_THREADS;
+            float dv[DL];
 #pragma unroll
-                    for (int off = 16; off >= COP; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane < COP && o < g.Co) atomicAdd(&bsum[o], s);
+            for (int i = 0; i < DL; ++i) {
+                const int idx = tid + i * M_THREADS;
+                int pos, o;
+                if (dy_ncdhw) { pos = idx % M_NB; o = idx / M_NB; } else { o = idx % COP; pos = idx / COP; }
+                const int lx = pos % MB_X, ly = (pos / MB_X) % MB_Y, lz = pos / (MB_X * MB_Y);
+                const int z = z0 + lz, yy = y0 + ly, x = x0c + lx;
+                dv[i] = 0.f;
+                if (idx < M_NB * COP && o < g.Co && z < g.D && yy < g.H && x < g.W) {
+                    const int64_t sp = ((int64_t)z * g.H + yy) * g.W + x;
+                    dv[i] = __ldg(dy_ncdhw ? dy + ((int64_t)b * g.Co + o) * S + sp : dy + ((int64_t)b * S + sp) * g.Co + o);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < DL; ++i) {
+                const int idx = tid + i * M_THREADS;
+                if (idx >= M_NB * COP) continue;          // whole warps drop out together (M_NB * COP % 32 == 0)
+                int pos, o;
+                if (dy_ncdhw) { pos = idx % M_NB; o = idx / M_NB; } else { o = idx % COP; pos = idx / COP; }
+                dYs[pos * DS + o] = to_tf32(dv[i]);
+                if (want_bias) {
+                    // lanes of a warp share o (NCDHW: 128 % 32 == 0) or hold o = lane % COP (channels-last)
+                    float s = dv[i];
+                    if (dy_ncdhw) {
+                        s = warp_sum(s);
+                        if (lane == 0 && o < g.Co) atomicAdd(&bsum[o], s);
+                    } else {
+#pragma unroll
+                        for (int off = 16; off >= COP; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                        if (lane < COP && o < g.Co) atomicAdd(&bsum[o], s);
+                    }
                 }
             }
         }

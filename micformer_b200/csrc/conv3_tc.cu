@@ -5,15 +5,18 @@
 //   y[p, n] = bias[n] + sum_{tap} sum_{c} x[p + tap, c] * Wsrc[tap'][n][c]     (M = positions, N tile = 16 | 32, K = 27 * Cin)
 //
 // No im2col and no per-tap re-fetch: a CTA owns an (8 x 16) x/y footprint and marches over a z segment.  Each
-// input z-plane of the footprint (+1 halo: 10 x 18 positions) is staged ONCE per 16-channel chunk into a 4-slot
+// input z-plane of the footprint (+1 halo: 10 x 18 positions) is staged ONCE per 8-channel chunk into an 8-slot
 // shared-memory ring in the tcgen05 "no swizzle" K-major core-matrix layout
 //     plane[kj][pos][4 floats]      (kj = 4-channel group, pos = y'*10 + x' in the haloed plane)
 // so that all 27 taps are just different START ADDRESSES of the same staged data: tap (tz,ty,tx) reads ring slot
 // z+tz at byte offset (ty*10 + tx)*16 with SBO = 160 B (next y row = next 8-row core-matrix group) and LBO = 2880 B
-// (next 4-channel group).  One tcgen05.mma (M=128, N=16, K=8 tf32) per (tap, 8 channels); the Dz output planes of
-// the segment accumulate in Dz*16 TMEM columns across all channel chunks.  Operands are rounded to nearest TF32
-// while being staged.  Producer / epilogue: 4 warps (coalesced float4 gathers, zero fill outside the volume);
-// MMA: 1 elected lane of warp 4.
+// (next 4-channel group).  One tcgen05.mma (M=128, N=NT, K=8 tf32) per (tap, chunk); the Dz output planes of
+// the segment accumulate in Dz*NT TMEM columns across all channel chunks.
+//
+// Producers (4 warps) move every 16-byte element with cp.async (zero-fill outside the volume), five plane-chunks
+// ahead of the one being finished, then round their own elements to nearest TF32 in shared memory (the tensor core
+// truncates) and publish the plane through an mbarrier; the MMA issuer is one elected lane of warp 4; the producer
+// warps drain TMEM at the end.  Small grids are split over channel chunks (grid.z) with an atomic epilogue.
 #include "common.cuh"
 
 namespace mic {
@@ -21,12 +24,13 @@ namespace mic {
 constexpr int TX = 8, TY = 16;                 // footprint (x, y) -> 128 output positions per plane (UMMA M)
 constexpr int HXS = TX + 2, HYS = TY + 2;      // haloed plane
 constexpr int PPOS = HXS * HYS;                // 180 positions per staged plane
-constexpr int RING = 4;
+constexpr int KJ = 2;                          // 4-channel groups per K chunk (8 input channels = one MMA K step)
+constexpr int CCH = 4 * KJ;
+constexpr int PLANE_BYTES = KJ * PPOS * 16;    // 5760
+constexpr int RING = 8;
+constexpr int AHEAD = RING - 3;                // plane-chunks in flight ahead of the one being published
+constexpr int PL = (PPOS * KJ + 127) / 128;    // 16-byte elements per producer thread per plane-chunk (3)
 constexpr int CT_THREADS = 160;
-// template parameters of the kernel: KJ = 4-channel groups per K chunk (chunk = 4*KJ input channels: 16, or 8 for the
-// 8-channel dy of out_conv's backward), NT = output channels per CTA (UMMA N).
-//   plane slot  : KJ * PPOS * 16 bytes            [kj][pos][4 floats]
-//   weight chunk: 27 * KJ * NT * 16 bytes         [tap][kj][n][4 floats]
 
 struct ConvTcGeom {
     int B, D, H, W;
@@ -34,7 +38,8 @@ struct ConvTcGeom {
     int N0, N1;            // output channels: y0 | y1 (channels-last), or N0 planes of an NCDHW tensor (out_ncdhw)
     int acc0, acc1;        // accumulate into y0 / y1 instead of storing
     int in_ncdhw, out_ncdhw, flip;
-    int Dz, nseg, nfy, nfx, nwb;
+    int Dz, nseg, nfy, nfx;
+    int ksplit, cps;       // channel-chunk splits (grid.z) and chunks per split; ksplit > 1 -> atomic epilogue
 };
 
 __device__ __forceinline__ uint32_t csmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,17 +86,28 @@ __device__ __forceinline__ float rna_tf32(float x) {
 }
 __device__ __forceinline__ float4 rna4(float4 v) { return make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w)); }
 
-template <int KJ, int NT>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void round_smem16(uint8_t* p) {
+    float4* q = reinterpret_cast<float4*>(p);
+    *q = rna4(*q);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(CT_THREADS, NT == 16 ? 3 : 2)
 conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ Wsrc,
                 const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, ConvTcGeom g, int tcols) {
-    constexpr int CCH = 4 * KJ;
-    constexpr int PLANE_BYTES = KJ * PPOS * 16;
     constexpr int W_BYTES = 27 * KJ * NT * 16;
+    constexpr int WL = (27 * NT * KJ + 127) / 128;         // 16-byte weight elements per producer thread per chunk
     extern __shared__ __align__(128) uint8_t csm[];
-    uint8_t* ring = csm;                                   // RING planes
-    uint8_t* wbuf = csm + RING * PLANE_BYTES;              // nwb weight buffers
-    uint64_t* pfull = reinterpret_cast<uint64_t*>(wbuf + g.nwb * W_BYTES);
+    uint8_t* ring = csm;                                   // RING plane-chunks
+    uint8_t* wbuf = csm + RING * PLANE_BYTES;              // 2 weight buffers
+    uint64_t* pfull = reinterpret_cast<uint64_t*>(wbuf + 2 * W_BYTES);
     uint64_t* pempty = pfull + RING;
     uint64_t* wfull = pempty + RING;
     uint64_t* wempty = wfull + 2;
@@ -102,8 +118,9 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     const int Cin = g.C0 + g.C1;
     const int Ntot = g.N0 + g.N1;
     const int n0 = blockIdx.y * NT;                        // first output channel of this CTA
-    const int nchunks = (Cin + CCH - 1) / CCH;
-    const int nwb = g.nwb;
+    const int nchunks_all = (Cin + CCH - 1) / CCH;
+    const int ch_lo = blockIdx.z * g.cps;
+    const int nchunks = min(g.cps, nchunks_all - ch_lo);   // channel chunks of this CTA (>= 1 by construction)
     // tile decode: blockIdx.x = ((b*nseg + seg)*nfy + fy)*nfx + fx
     int t = blockIdx.x;
     const int fx = t % g.nfx; t /= g.nfx;
@@ -112,7 +129,8 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     const int b = t;
     const int xb = fx * TX, yb = fy * TY, zs = seg * g.Dz;
     const int nz = min(g.Dz, g.D - zs);                    // output planes of this segment
-    const int planes_per_chunk = nz + 2;
+    const int ppc = nz + 2;                                // staged planes per chunk
+    const int total = nchunks * ppc;                       // plane-chunks of this CTA
     const int64_t S = (int64_t)g.D * g.H * g.W;
 
     if (threadIdx.x == 0) {
@@ -133,90 +151,95 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     if (warp < 4) {
         // ------------------------------------------------------------------ producers
         const int tid = threadIdx.x;     // 0..127
-        int n = 0;                       // running plane counter (ring position)
-        constexpr int PL = (PPOS * KJ + 127) / 128;          // float4 gathers per thread per plane
-        constexpr int WL = (27 * NT * KJ + 127) / 128;       // float4 loads per thread per weight chunk
-        // gather one haloed plane chunk into registers (all loads in flight before the first use)
-        auto gather = [&](int z, int c0, float4 (&r)[PL]) {
+        const uint32_t ring_u32 = csmem_u32(ring), wbuf_u32 = csmem_u32(wbuf);
+        // this thread's elements of a plane-chunk: element e = tid + i*128 -> (kj = e % KJ, pos = e / KJ)
+        int e_off[PL], e_dy[PL], e_dx[PL];
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            const int e = tid + i * 128;
+            const int kj = e % KJ, pos = e / KJ;
+            e_off[i] = e < PPOS * KJ ? (kj * PPOS + pos) * 16 : -1;
+            e_dy[i] = yb + pos / HXS - 1;
+            e_dx[i] = xb + pos % HXS - 1;
+        }
+        // issue the copies of plane-chunk n (and, on the first plane of a chunk, that chunk's weights)
+        auto issue = [&](int n) {
+            const int ch = n / ppc, pz = n - ch * ppc;
+            const int c0 = (ch_lo + ch) * CCH;
+            const int z = zs - 1 + pz;
+            const int slot = n % RING;
+            cbar_wait(&pempty[slot], ((n / RING) & 1) ^ 1);
             const bool zok = z >= 0 && z < g.D;
+            const uint32_t sbase = ring_u32 + slot * PLANE_BYTES;
 #pragma unroll
             for (int i = 0; i < PL; ++i) {
-                const int idx = tid + i * 128;
-                const int kj = idx % KJ, pos = idx / KJ;
-                const int yy = yb + pos / HXS - 1, xx = xb + pos % HXS - 1;
-                const int c = c0 + kj * 4;
-                r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < PPOS * KJ && zok && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W && c < Cin) {
-                    if (g.in_ncdhw) {
-                        const float* src = x0 + ((int64_t)b * Cin + c) * S + ((int64_t)z * g.H + yy) * g.W + xx;
-                        r[i].x = src[0];
-                        if (c + 1 < Cin) r[i].y = src[S];
-                        if (c + 2 < Cin) r[i].z = src[2 * S];
-                        if (c + 3 < Cin) r[i].w = src[3 * S];
-                    } else {
+                if (e_off[i] < 0) continue;
+                const int c = c0 + ((tid + i * 128) % KJ) * 4;
+                const int yy = e_dy[i], xx = e_dx[i];
+                const bool ok = zok && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W && c < Cin;
+                if (g.in_ncdhw) {
+                    const float* src = ok ? x0 + ((int64_t)b * Cin + c) * S + ((int64_t)z * g.H + yy) * g.W + xx : x0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cp_async4(sbase + e_off[i] + 4 * j, ok && c + j < Cin ? src + j * S : x0, ok && c + j < Cin);
+                } else {
+                    const float* src = x0;
+                    if (ok) {
                         const int64_t row = (((int64_t)b * g.D + z) * g.H + yy) * g.W + xx;
-                        r[i] = c < g.C0 ? *reinterpret_cast<const float4*>(x0 + row * g.C0 + c)
-                                        : *reinterpret_cast<const float4*>(x1 + row * g.C1 + (c - g.C0));
+                        src = c < g.C0 ? x0 + row * g.C0 + c : x1 + row * g.C1 + (c - g.C0);
                     }
+                    cp_async16(sbase + e_off[i], src, ok);
                 }
             }
-        };
-        float4 cur[PL], nxt[PL];
-        gather(zs - 1, 0, cur);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int c0 = ch * CCH;
-            // weights of this chunk: smem [tap][kj][n][4] <- Wsrc[tap'][n0 + n][c0 + 4 kj ..]
-            {
-                const int wb = ch % nwb;
-                float4 wr[WL];
+            if (pz == 0) {
+                const int wb = ch & 1;
+                cbar_wait(&wempty[wb], ((ch >> 1) & 1) ^ 1);
 #pragma unroll
                 for (int i = 0; i < WL; ++i) {
                     const int idx = tid + i * 128;
+                    if (idx >= 27 * NT * KJ) continue;
                     const int kj = idx % KJ, o = (idx / KJ) % NT, tap = idx / (KJ * NT);
                     const int c = c0 + kj * 4;
-                    wr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < 27 * NT * KJ && n0 + o < Ntot && c < Cin) {
-                        const int ts = g.flip ? 26 - tap : tap;
-                        const float* src = Wsrc + ((int64_t)ts * Ntot + n0 + o) * Cin + c;
-                        if ((Cin & 3) == 0) wr[i] = *reinterpret_cast<const float4*>(src);
-                        else {
-                            wr[i].x = src[0];
-                            if (c + 1 < Cin) wr[i].y = src[1];
-                            if (c + 2 < Cin) wr[i].z = src[2];
-                            if (c + 3 < Cin) wr[i].w = src[3];
-                        }
-                    }
+                    const bool ok = n0 + o < Ntot && c < Cin;
+                    const int ts = g.flip ? 26 - tap : tap;
+                    cp_async16(wbuf_u32 + wb * W_BYTES + ((tap * KJ + kj) * NT + o) * 16,
+                               ok ? Wsrc + ((int64_t)ts * Ntot + n0 + o) * Cin + c : Wsrc, ok);
                 }
-                cbar_wait(&wempty[wb], ((ch / nwb) & 1) ^ 1);
-                float4* wd = reinterpret_cast<float4*>(wbuf + wb * W_BYTES);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // look-ahead: a chunk's weights are copied with its first plane and wait for the chunk two before to retire, so
+        // the producer may not run further ahead than one chunk plus one plane (else it would wait on its own output)
+        const int ahead = min(AHEAD, ppc + 1);                 // 4 or 5
+        for (int n = 0; n < ahead; ++n) {
+            if (n < total) issue(n);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int n = 0; n < total; ++n) {
+            // groups committed so far: ahead + n; plane-chunk n is group n
+            if (ahead == AHEAD) asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 2) : "memory");
+            const int ch = n / ppc, pz = n - ch * ppc;
+            const int slot = n % RING;
+            uint8_t* sbase = ring + slot * PLANE_BYTES;
+#pragma unroll
+            for (int i = 0; i < PL; ++i)
+                if (e_off[i] >= 0) round_smem16(sbase + e_off[i]);
+            if (pz == 0) {
+                const int wb = ch & 1;
 #pragma unroll
                 for (int i = 0; i < WL; ++i) {
                     const int idx = tid + i * 128;
+                    if (idx >= 27 * NT * KJ) continue;
                     const int kj = idx % KJ, o = (idx / KJ) % NT, tap = idx / (KJ * NT);
-                    if (idx < 27 * NT * KJ) wd[(tap * KJ + kj) * NT + o] = rna4(wr[i]);
+                    round_smem16(wbuf + wb * W_BYTES + ((tap * KJ + kj) * NT + o) * 16);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 cbar_arrive(&wfull[wb]);
             }
-            for (int pz = 0; pz < planes_per_chunk; ++pz, ++n) {
-                // prefetch the next plane (possibly the first plane of the next chunk) while this one is stored
-                const bool last_plane = pz + 1 == planes_per_chunk;
-                if (!last_plane) gather(zs + pz, c0, nxt);
-                else if (ch + 1 < nchunks) gather(zs - 1, c0 + CCH, nxt);
-                const int slot = n % RING;
-                cbar_wait(&pempty[slot], ((n / RING) & 1) ^ 1);
-                float4* pd = reinterpret_cast<float4*>(ring + slot * PLANE_BYTES);
-#pragma unroll
-                for (int i = 0; i < PL; ++i) {
-                    const int idx = tid + i * 128;
-                    const int kj = idx % KJ, pos = idx / KJ;
-                    if (idx < PPOS * KJ) pd[kj * PPOS + pos] = rna4(cur[i]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                cbar_arrive(&pfull[slot]);
-#pragma unroll
-                for (int i = 0; i < PL; ++i) cur[i] = nxt[i];
-            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            cbar_arrive(&pfull[slot]);
+            if (n + ahead < total) issue(n + ahead);
+            else asm volatile("cp.async.commit_group;" ::: "memory");          // keep the group count uniform
         }
         // ------------------------------------------------------------------ epilogue
         cbar_wait(accdone, 0);
@@ -225,6 +248,8 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
         const int r = q * 32 + lane;                          // row in the 128-position plane tile
         const int yy = yb + r / TX, xx = xb + r % TX;
         const bool ok = yy < g.H && xx < g.W;
+        const bool atomic = g.ksplit > 1;
+        const bool add_bias = bias != nullptr && blockIdx.z == 0;
         for (int zi = 0; zi < nz; ++zi) {
             const int z = zs + zi;
             const int64_t sp = ((int64_t)z * g.H + yy) * g.W + xx;
@@ -241,11 +266,14 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
                 if (!ok) continue;
                 const int nb = n0 + gi * 16;
                 if (g.out_ncdhw) {
-                    for (int o = 0; o < 16 && nb + o < Ntot; ++o) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        if (nb + o >= Ntot) continue;
                         float* dst = y0 + ((int64_t)b * Ntot + nb + o) * S + sp;
-                        float val = __uint_as_float(v[o]) + (bias ? bias[nb + o] : 0.f);
-                        if (g.acc0) val += *dst;
-                        *dst = val;
+                        const float val = __uint_as_float(v[o]) + (add_bias ? bias[nb + o] : 0.f);
+                        if (atomic) atomicAdd(dst, val);
+                        else if (g.acc0) *dst += val;
+                        else *dst = val;
                     }
                 } else {
 #pragma unroll
@@ -254,7 +282,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
                         if (c >= Ntot) continue;
                         float4 val = make_float4(__uint_as_float(v[o4 * 4]), __uint_as_float(v[o4 * 4 + 1]),
                                                  __uint_as_float(v[o4 * 4 + 2]), __uint_as_float(v[o4 * 4 + 3]));
-                        if (bias) {
+                        if (add_bias) {
                             const float4 bb = *reinterpret_cast<const float4*>(bias + c);
                             val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
                         }
@@ -262,11 +290,14 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
                         int accf;
                         if (c < g.N0) { dst = reinterpret_cast<float4*>(y0 + ((int64_t)b * S + sp) * g.N0 + c); accf = g.acc0; }
                         else { dst = reinterpret_cast<float4*>(y1 + ((int64_t)b * S + sp) * g.N1 + (c - g.N0)); accf = g.acc1; }
-                        if (accf) {
-                            const float4 old = *dst;
-                            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                        if (atomic) atomicAdd(dst, val);
+                        else {
+                            if (accf) {
+                                const float4 old = *dst;
+                                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                            }
+                            *dst = val;
                         }
-                        *dst = val;
                     }
                 }
             }
@@ -276,14 +307,12 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t ring_addr = csmem_u32(ring), w_addr = csmem_u32(wbuf);
         int n0p = 0;
-        for (int ch = 0; ch < nchunks; ++ch, n0p += planes_per_chunk) {
-            const int wb = ch % nwb;
-            cbar_wait(&wfull[wb], (ch / nwb) & 1);
-            const int cvalid = min(CCH, Cin - ch * CCH);
-            const int ksteps = (cvalid + 7) / 8;                 // K = 8 channels per MMA
-            int waited = n0p - 1;                                 // highest plane index already waited for
+        for (int ch = 0; ch < nchunks; ++ch, n0p += ppc) {
+            const int wb = ch & 1;
+            cbar_wait(&wfull[wb], (ch >> 1) & 1);
+            int waited = n0p - 1;                                 // highest plane-chunk index already waited for
             for (int zi = 0; zi < nz; ++zi) {
-                const int need = n0p + zi + 2;                    // planes n0p+zi .. n0p+zi+2
+                const int need = n0p + zi + 2;                    // plane-chunks n0p+zi .. n0p+zi+2
                 while (waited < need) {
                     ++waited;
                     cbar_wait(&pfull[waited % RING], (waited / RING) & 1);
@@ -297,11 +326,9 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
 #pragma unroll
                         for (int tx = 0; tx < 3; ++tx) {
                             const int tap = (tz * 3 + ty) * 3 + tx;
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint64_t ad = cdesc(pbase + (uint32_t)((ty * HXS + tx) * 16 + 2 * ks * PPOS * 16), PPOS * 16, HXS * 16);
-                                const uint64_t bd = cdesc(w_addr + (uint32_t)(wb * W_BYTES + (tap * KJ + 2 * ks) * NT * 16), NT * 16, 128);
-                                cmma(dcol, ad, bd, idesc, (ch | tap | ks) ? 1u : 0u);
-                            }
+                            const uint64_t ad = cdesc(pbase + (uint32_t)((ty * HXS + tx) * 16), PPOS * 16, HXS * 16);
+                            const uint64_t bd = cdesc(w_addr + (uint32_t)(wb * W_BYTES + tap * KJ * NT * 16), NT * 16, 128);
+                            cmma(dcol, ad, bd, idesc, (ch | tap) ? 1u : 0u);
                         }
                 }
                 ccommit(&pempty[(n0p + zi) % RING]);              // plane z-1 is no longer needed
@@ -320,62 +347,77 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     }
 }
 
-template <int KJ, int NT>
+// zero_out: y must be all zeros on entry when the launch splits the channel chunks (atomic epilogue); returned through
+// *needs_zero so that callers that own a fresh buffer can clear it themselves
+template <int NT>
 static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, const float* bias, float* y0, float* y1,
-                          ConvTcGeom g, cudaStream_t st, const char* who) {
+                          ConvTcGeom g, bool allow_split, cudaStream_t st, const char* who) {
     const int Cin = g.C0 + g.C1, Ntot = g.N0 + g.N1;
-    const int nchunks = (Cin + 4 * KJ - 1) / (4 * KJ);
+    const int nchunks = (Cin + CCH - 1) / CCH;
     const int nych = (Ntot + NT - 1) / NT;
-    g.nfy = g.H / TY; g.nfx = g.W / TX;
-    g.nwb = nchunks > 1 ? 2 : 1;
+    g.nfy = (g.H + TY - 1) / TY; g.nfx = (g.W + TX - 1) / TX;
     const int foot = g.B * g.nfy * g.nfx;
-    // z segment length: enough CTAs to fill the GPU; Dz * NT accumulator columns, two CTAs per SM share 512
-    int Dz = 256 / NT;
-    while (Dz > 2 && (int64_t)foot * ((g.D + Dz - 1) / Dz) * nych < 2 * num_sms()) Dz >>= 1;
+    const int target = 2 * num_sms();
+    // z segment length: enough CTAs to fill the GPU; Dz * NT accumulator columns, 3 (NT=16) or 2 (NT=32) CTAs per SM
+    int Dz = 8;
+    while (Dz > 2 && (int64_t)foot * ((g.D + Dz - 1) / Dz) * nych < target) Dz >>= 1;
     if (Dz > g.D) Dz = g.D;
     g.Dz = Dz; g.nseg = (g.D + Dz - 1) / Dz;
+    const int64_t base = (int64_t)foot * g.nseg * nych;
+    int ksplit = 1;
+    if (allow_split && base < target) {
+        ksplit = (int)((target + base - 1) / base);
+        if (ksplit > nchunks) ksplit = nchunks;
+    }
+    g.cps = (nchunks + ksplit - 1) / ksplit;
+    g.ksplit = (nchunks + g.cps - 1) / g.cps;
     int tcols = 32;
     while (tcols < Dz * NT) tcols <<= 1;
-    const size_t smem = RING * (KJ * PPOS * 16) + g.nwb * (27 * KJ * NT * 16) + 256;
+    const size_t smem = RING * PLANE_BYTES + 2 * (27 * KJ * NT * 16) + 256;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv3_tc_kernel<KJ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             RING * (KJ * PPOS * 16) + 2 * (27 * KJ * NT * 16) + 256);
+        cudaFuncSetAttribute(conv3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    dim3 grid((unsigned)((int64_t)foot * g.nseg), (unsigned)nych);
-    conv3_tc_kernel<KJ, NT><<<grid, CT_THREADS, smem, st>>>(x0, x1, Wsrc, bias, y0, y1, g, tcols);
+    if (g.ksplit > 1) {
+        // atomic epilogue: the destination starts from zero (bias is added by split 0)
+        const size_t bytes = (size_t)g.B * g.D * g.H * g.W * sizeof(float);
+        cudaError_t e = cudaMemsetAsync(y0, 0, bytes * g.N0, st);
+        if (e == cudaSuccess && y1) e = cudaMemsetAsync(y1, 0, bytes * g.N1, st);
+        if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "%s memset: %s", who, cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)((int64_t)foot * g.nseg), (unsigned)nych, (unsigned)g.ksplit);
+    conv3_tc_kernel<NT><<<grid, CT_THREADS, smem, st>>>(x0, x1, Wsrc, bias, y0, y1, g, tcols);
     return check_launch(who);
 }
 
 static bool misaligned16(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15); }
 
-// returns MIC_ERR_UNSUPPORTED when the geometry is not taken (caller falls back to the CUDA-core kernel)
+// returns MIC_ERR_UNSUPPORTED when the arguments are not taken (caller falls back to the CUDA-core kernel)
 int tc_conv3_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias, float* y, int B,
                  int D, int H, int W, int Co, int out_ncdhw, cudaStream_t st) {
-    if (W % TX || H % TY || Co > 16 || Co < 1 || (C0 & 3) || (C1 & 3) || (!out_ncdhw && (Co & 3))) return MIC_ERR_UNSUPPORTED;
+    if (Co > 16 || Co < 1 || (C0 & 3) || (C1 & 3) || (!out_ncdhw && (Co & 3))) return MIC_ERR_UNSUPPORTED;
     if (misaligned16(x0) || misaligned16(x1) || misaligned16(Wk) || misaligned16(y) || misaligned16(bias)) return MIC_ERR_UNSUPPORTED;
     ConvTcGeom g{};
     g.B = B; g.D = D; g.H = H; g.W = W; g.C0 = C0; g.C1 = C1; g.N0 = Co; g.N1 = 0;
     g.out_ncdhw = out_ncdhw;
-    return launch_conv_tc<4, 16>(x0, x1, Wk, bias, y, nullptr, g, st, "conv3_tc_kernel<fwd>");
+    return launch_conv_tc<16>(x0, x1, Wk, bias, y, nullptr, g, true, st, "conv3_tc_kernel<fwd>");
 }
 
 // dx0 | dx1 (channels-last, C0 | C1 channels) (+)= conv3^T(dy; Wt) with Wt = [27][C0 + C1][Co]; dy has Co channels,
 // channels-last or NCDHW
 int tc_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1, int acc1, int B,
                       int D, int H, int W, int Co, int dy_ncdhw, cudaStream_t st) {
-    if (W % TX || H % TY || (Co != 8 && Co != 16) || (C0 & 3) || (C1 & 3) || C0 + C1 < 16) return MIC_ERR_UNSUPPORTED;
+    if ((Co != 8 && Co != 16) || (C0 & 3) || (C1 & 3) || C0 + C1 < 16) return MIC_ERR_UNSUPPORTED;
     if (misaligned16(dy) || misaligned16(Wt) || misaligned16(dx0) || misaligned16(dx1)) return MIC_ERR_UNSUPPORTED;
     ConvTcGeom g{};
     g.B = B; g.D = D; g.H = H; g.W = W; g.C0 = Co; g.C1 = 0; g.N0 = C0; g.N1 = C1; g.acc0 = acc0; g.acc1 = acc1;
     g.in_ncdhw = dy_ncdhw; g.flip = 1;
-    if (Co == 8) return launch_conv_tc<2, 32>(dy, nullptr, Wt, nullptr, dx0, dx1, g, st, "conv3_tc_kernel<bwd_data,8>");
-    return launch_conv_tc<4, 32>(dy, nullptr, Wt, nullptr, dx0, dx1, g, st, "conv3_tc_kernel<bwd_data,16>");
+    // the accumulate flags rule out a zero-initialised atomic epilogue: no channel-chunk split (K = Co is 1-2 chunks anyway)
+    return launch_conv_tc<32>(dy, nullptr, Wt, nullptr, dx0, dx1, g, false, st, "conv3_tc_kernel<bwd_data>");
 }
 
 }  // namespace mic
-
 extern "C" int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias,
                                 float* y, int B, int D, int H, int W, int Co, int out_ncdhw, void* stream) {
     MIC_REQUIRE(x0 && Wk && y && (C1 == 0 || x1), "conv3_tc_fwd: null pointer");

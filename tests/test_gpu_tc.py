@@ -155,7 +155,11 @@ def test_tc_w7_model_logits(tc_mode):
 @pytest.mark.parametrize("C0,C1,Co,dims,ncdhw", [(48, 48, 16, (8, 32, 32), False),      # conv_offset, stage-0 planes
                                                  (96, 96, 16, (16, 16, 16), False),     # conv_offset, stage 1
                                                  (24, 0, 8, (12, 32, 16), True),        # out_conv (NCDHW logits / dlogits)
-                                                 (32, 0, 16, (5, 16, 8), False)])
+                                                 (32, 0, 16, (5, 16, 8), False),
+                                                 (192, 192, 16, (8, 8, 8), False),      # stage 2: half-empty footprint, K split
+                                                 (384, 384, 16, (4, 4, 4), False),      # stage 3
+                                                 (24, 24, 16, (7, 7, 7), False),        # odd sizes (window-7 padded grids)
+                                                 (16, 0, 8, (3, 20, 9), True)])
 def test_tc_conv3_fwd_bwd(tc_mode, C0, C1, Co, dims, ncdhw):
     """tcgen05 implicit-GEMM 3x3x3 conv: forward, backward-data (mirrored taps through the same kernel, accumulate
     epilogue) and backward-weight against F.conv3d autograd in fp64."""
