@@ -305,25 +305,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
         if (warp >= 6) goto teardown;           // converter-only warps
-        if (nkb > 0) {
-            mbar_wait(tmem_full, 0);
-            tc_fence_after();
-        }
-        if (warp == 2 && lane == 0) trace(6);
         // Drain: TMEM -> registers -> fused epilogue math -> 128B-swizzled staging tile in shared memory (the operand
         // ring is free once tmem_full fired) -> one TMA store (or TMA reduce-add for accumulate / split-R) per
         // 32-column chunk.  TMA clips rows >= I and columns >= J, so ragged edges need no store guards.
+        // Global operands of the epilogue are fetched BEFORE waiting for the accumulator: the bias tile goes to shared
+        // memory once, the residual / pre-activation row is software-pipelined one chunk ahead.
         const bool row_ok = gi < e.I;
         float rs = e.rowscale_r ? e.rowscale_r[(int64_t)kb0 * TKB / e.rps_r] : 1.f;
         if (row_ok && e.rowscale_i) rs *= e.rowscale_i[gi / e.rps_i];
         const bool use_bias = e.bias != nullptr && blockIdx.z == 0;
+        float* sbias = reinterpret_cast<float*>(smem + (e.split3 ? 12 : 6) * A_BYTES + 256);
+        if (use_bias) {
+            const int tt = (warp - 2) * 32 + lane;               // 0..127 >= BNT columns of this tile
+            if (tt < BNT) sbias[tt] = j0 + tt < e.J ? e.bias[j0 + tt] : 0.f;
+        }
         const int64_t gi64 = gi;
         const float* aux = nullptr;          // EPI 2: residual row, EPI 3: pre-activation row
         if (EPI == 2) aux = e.res + gi64 * e.ldres;
         if (EPI == 3) aux = e.mulgrad + gi64 * e.ldmg;
         const int64_t ldaux = EPI == 2 ? e.ldres : e.ldmg;
         const bool aux_al = aux && ((reinterpret_cast<uintptr_t>(aux) | (uintptr_t)(ldaux * 4)) & 15) == 0 && (j0 & 3) == 0;
-        const bool bias_al = use_bias && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0 && (j0 & 3) == 0;
+        auto load_aux = [&](int c0, float4 (&av)[8]) {
+            const int gj0 = j0 + c0;
+            const int ncol = min(32, min(BNT - c0, e.J - gj0));
+            if ((EPI == 2 || EPI == 3) && row_ok) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (aux_al && 4 * t + 3 < ncol) av[t] = __ldg(reinterpret_cast<const float4*>(aux + gj0 + 4 * t));
+                    else {
+                        av[t].x = 4 * t + 0 < ncol ? aux[gj0 + 4 * t + 0] : 0.f;
+                        av[t].y = 4 * t + 1 < ncol ? aux[gj0 + 4 * t + 1] : 0.f;
+                        av[t].z = 4 * t + 2 < ncol ? aux[gj0 + 4 * t + 2] : 0.f;
+                        av[t].w = 4 * t + 3 < ncol ? aux[gj0 + 4 * t + 3] : 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) av[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 av[8];
+        load_aux(0, av);
+        if ((EPI == 2 || EPI == 3) && row_ok) {
+            // the rest of this thread's row segment: pull the lines towards L1 while the accumulator finishes
+            for (int c = 32; c < BNT && j0 + c < e.J; c += 32)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(aux + j0 + c));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // bias tile visible to the four epilogue warps
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        if (warp == 2 && lane == 0) trace(6);
         const int row = q * 32 + lane;                    // row inside the 128-row tile
         const bool want_pre = EPI == 1 && e.pre != nullptr;
         int nchunk = 0;
@@ -342,34 +375,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // EPI 1 additionally stages the pre-activation in slot 3 + c (BNT <= 96 there)
             uint8_t* cbuf = smem + nchunk * 16384;
             uint8_t* pbuf = smem + (3 + nchunk) * 16384;
-            float4 av[8];
-            if ((EPI == 2 || EPI == 3) && row_ok) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (aux_al && 4 * t + 3 < ncol) av[t] = *reinterpret_cast<const float4*>(aux + gj0 + 4 * t);
-                    else {
-                        av[t].x = 4 * t + 0 < ncol ? aux[gj0 + 4 * t + 0] : 0.f;
-                        av[t].y = 4 * t + 1 < ncol ? aux[gj0 + 4 * t + 1] : 0.f;
-                        av[t].z = 4 * t + 2 < ncol ? aux[gj0 + 4 * t + 2] : 0.f;
-                        av[t].w = 4 * t + 3 < ncol ? aux[gj0 + 4 * t + 3] : 0.f;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) av[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 float x[4] = {v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]};
                 if (use_bias) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bias_al && 4 * t + 3 < ncol) b4 = *reinterpret_cast<const float4*>(e.bias + gj0 + 4 * t);
-                    else {
-                        if (4 * t + 0 < ncol) b4.x = e.bias[gj0 + 4 * t + 0];
-                        if (4 * t + 1 < ncol) b4.y = e.bias[gj0 + 4 * t + 1];
-                        if (4 * t + 2 < ncol) b4.z = e.bias[gj0 + 4 * t + 2];
-                        if (4 * t + 3 < ncol) b4.w = e.bias[gj0 + 4 * t + 3];
-                    }
+                    const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * t);
                     x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
                 }
                 const uint32_t soff = (uint32_t)row * 128u + ((uint32_t)(t ^ (row & 7)) << 4);
@@ -387,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (EPI == 2) { x[0] += av[t].x; x[1] += av[t].y; x[2] += av[t].z; x[3] += av[t].w; }
                 *reinterpret_cast<float4*>(cbuf + soff) = make_float4(x[0], x[1], x[2], x[3]);
             }
+            if (c0 + 32 < BNT) load_aux(c0 + 32, av);               // next chunk's row segment: in flight across the store
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && lane == 0 && ncol > 0) {
@@ -408,6 +419,296 @@ teardown:
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
     }
     if (threadIdx.x == 32) trace(9);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Large problems (several tiles per SM): one CTA per SM walks its tiles; the drain of tile n (TMEM -> epilogue ->
+// staging -> TMA store) overlaps the loads / operand conditioning / MMAs of tile n+1 through two TMEM accumulators and
+// a dedicated double-buffered staging area, so the per-tile latency chain of the one-shot kernel (prologue, first TMA
+// round trip, epilogue) is paid once per CTA instead of once per tile.
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: epilogue   warps 6-13: operand converters
+constexpr int TCP_THREADS = 448;
+constexpr int TCP_CONV = 256;            // converter threads (warps 6..13)
+
+struct TcpSched {
+    int tiles_i, tiles_j, splits, ntiles;
+    int nst;                             // ring stages
+    int stage_slots;                     // 16 KB slots per stage (2, or 4 with the 3xTF32 lo tiles)
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+gemm_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapP, TcEpi e, TcpSched sc,
+                int BNT, int TCOLS) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int SLOT = TM * TKB * 4;                        // 16 KB
+    const int b_groups = (BNT + 31) / 32;
+    const int B_BYTES = (B_MN ? b_groups * 32 : BNT) * TKB * 4;
+    const int NST = sc.nst;
+    const int STG = sc.stage_slots * SLOT;                    // bytes per stage: [A | B | (Alo | Blo)]
+    uint8_t* ring = smem;
+    uint8_t* stage_c = smem + NST * STG;                      // 2 output staging slots
+    uint8_t* stage_p = stage_c + 2 * SLOT;                    // 2 pre-activation staging slots (EPI 1)
+    uint8_t* tail = stage_p + ((EPI == 1 && e.pre) ? 2 * SLOT : 0);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty = full + 8;
+    uint64_t* conv = empty + 8;
+    uint64_t* tmem_full = conv + 8;           // [2]
+    uint64_t* tmem_empty = tmem_full + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* sbias = reinterpret_cast<float*>(tail + 256);      // [2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_ij = sc.tiles_i * sc.tiles_j;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], TCP_CONV / 32); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> (j fastest: CTAs that run concurrently share the A tile in L2)
+    auto decode = [&](int t, int& i0, int& j0, int& kb0, int& nkb) {
+        const int z = t / tiles_ij;
+        const int r = t - z * tiles_ij;
+        const int ti = r / sc.tiles_j, tj = r - ti * sc.tiles_j;
+        i0 = ti * TM; j0 = tj * BNT;
+        kb0 = z * e.kb_per_split;
+        nkb = min(e.kb_total, kb0 + e.kb_per_split) - kb0;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            const uint32_t tx = SLOT + B_BYTES;
+            uint32_t cnt = 0;
+            for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+                int i0, j0, kb0, nkb;
+                decode(t, i0, j0, kb0, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                    const int s = cnt % NST;
+                    mbar_wait(&empty[s], ((cnt / NST) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], tx);
+                    const int r0 = (kb0 + kb) * TKB;
+                    uint8_t* a = ring + s * STG;
+                    uint8_t* b = a + SLOT;
+                    if (A_MN) {
+#pragma unroll
+                        for (int g = 0; g < TM / 32; ++g) tma_load_2d(a + g * 4096, &mapA, &full[s], i0 + g * 32, r0);
+                    } else {
+                        tma_load_2d(a, &mapA, &full[s], r0, i0);
+                    }
+                    if (B_MN) {
+                        for (int g = 0; g < b_groups; ++g) tma_load_2d(b + g * 4096, &mapB, &full[s], j0 + g * 32, r0);
+                    } else {
+                        tma_load_2d(b, &mapB, &full[s], r0, j0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            uint32_t cnt = 0, n = 0;
+            for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, ++n) {
+                int i0, j0, kb0, nkb;
+                decode(t, i0, j0, kb0, nkb);
+                const uint32_t buf = n & 1;
+                mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);        // epilogue drained the previous use
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * (uint32_t)TCOLS;
+                for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                    const int s = cnt % NST;
+                    mbar_wait(e.round_rn ? &conv[s] : &full[s], (cnt / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * STG);
+                    const uint32_t b_addr = a_addr + SLOT;
+#pragma unroll
+                    for (int k = 0; k < TKB / 8; ++k) {
+                        const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
+                        const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
+                        umma_tf32(dcol, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        if (e.split3) {
+                            const uint32_t al = a_addr + 2 * SLOT, bl = a_addr + 3 * SLOT;
+                            const uint64_t adl = A_MN ? make_desc(al + k * 1024, 4096, 512, 1) : make_desc(al + k * 32, 16, 1024, 2);
+                            const uint64_t bdl = B_MN ? make_desc(bl + k * 1024, 4096, 512, 1) : make_desc(bl + k * 32, 16, 1024, 2);
+                            umma_tf32(dcol, adl, bd, idesc, 1u);
+                            umma_tf32(dcol, ad, bdl, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp >= 6) {
+        // ---------------- operand converters (only when round_rn): nearest TF32 / hi-lo split of the landed tiles
+        if (e.round_rn) {
+            const int et = (warp - 6) * 32 + lane;
+            const int b_vec = B_BYTES / 16;
+            uint32_t cnt = 0;
+            for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+                int i0, j0, kb0, nkb;
+                decode(t, i0, j0, kb0, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                    const int s = cnt % NST;
+                    mbar_wait(&full[s], (cnt / NST) & 1);
+                    float4* a4 = reinterpret_cast<float4*>(ring + s * STG);
+                    float4* b4 = a4 + SLOT / 16;
+                    auto rn = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+                    if (e.split3) {
+                        float4* al4 = a4 + 2 * (SLOT / 16);
+                        float4* bl4 = a4 + 3 * (SLOT / 16);
+#pragma unroll 4
+                        for (int i = et; i < SLOT / 16; i += TCP_CONV) {
+                            const float4 v = a4[i];
+                            const float4 h = make_float4(rn(v.x), rn(v.y), rn(v.z), rn(v.w));
+                            a4[i] = h;
+                            al4[i] = make_float4(rn(v.x - h.x), rn(v.y - h.y), rn(v.z - h.z), rn(v.w - h.w));
+                        }
+                        for (int i = et; i < b_vec; i += TCP_CONV) {
+                            const float4 v = b4[i];
+                            const float4 h = make_float4(rn(v.x), rn(v.y), rn(v.z), rn(v.w));
+                            b4[i] = h;
+                            bl4[i] = make_float4(rn(v.x - h.x), rn(v.y - h.y), rn(v.z - h.z), rn(v.w - h.w));
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = et; i < SLOT / 16; i += TCP_CONV) {
+                            const float4 v = a4[i];
+                            a4[i] = make_float4(rn(v.x), rn(v.y), rn(v.z), rn(v.w));
+                        }
+                        for (int i = et; i < b_vec; i += TCP_CONV) {
+                            const float4 v = b4[i];
+                            b4[i] = make_float4(rn(v.x), rn(v.y), rn(v.z), rn(v.w));
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps 2..5: warp q = warp % 4 owns TMEM lanes [32q, 32q+32)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool elected = warp == 2 && lane == 0;
+        const bool want_pre = EPI == 1 && e.pre != nullptr;
+        uint32_t n = 0, chunk = 0;
+        for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, ++n) {
+            int i0, j0, kb0, nkb;
+            decode(t, i0, j0, kb0, nkb);
+            const uint32_t buf = n & 1;
+            const int gi = i0 + row;
+            const bool row_ok = gi < e.I;
+            float rs = e.rowscale_r ? e.rowscale_r[(int64_t)kb0 * TKB / e.rps_r] : 1.f;
+            if (row_ok && e.rowscale_i) rs *= e.rowscale_i[gi / e.rps_i];
+            const bool use_bias = e.bias != nullptr && kb0 == 0;
+            float* sb = sbias + buf * 128;
+            if (use_bias) {
+                const int tt = (warp - 2) * 32 + lane;
+                if (tt < BNT) sb[tt] = j0 + tt < e.J ? e.bias[j0 + tt] : 0.f;
+            }
+            const float* aux = nullptr;
+            if (EPI == 2) aux = e.res + (int64_t)gi * e.ldres;
+            if (EPI == 3) aux = e.mulgrad + (int64_t)gi * e.ldmg;
+            const int64_t ldaux = EPI == 2 ? e.ldres : e.ldmg;
+            const bool aux_al = aux && ((reinterpret_cast<uintptr_t>(aux) | (uintptr_t)(ldaux * 4)) & 15) == 0 && (j0 & 3) == 0;
+            auto load_aux = [&](int c0, float4 (&av)[8]) {
+                const int gj0 = j0 + c0;
+                const int ncol = min(32, min(BNT - c0, e.J - gj0));
+                if ((EPI == 2 || EPI == 3) && row_ok) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (aux_al && 4 * u + 3 < ncol) av[u] = __ldg(reinterpret_cast<const float4*>(aux + gj0 + 4 * u));
+                        else {
+                            av[u].x = 4 * u + 0 < ncol ? aux[gj0 + 4 * u + 0] : 0.f;
+                            av[u].y = 4 * u + 1 < ncol ? aux[gj0 + 4 * u + 1] : 0.f;
+                            av[u].z = 4 * u + 2 < ncol ? aux[gj0 + 4 * u + 2] : 0.f;
+                            av[u].w = 4 * u + 3 < ncol ? aux[gj0 + 4 * u + 3] : 0.f;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            float4 av[8];
+            load_aux(0, av);                                   // in flight while the accumulator finishes
+            mbar_wait(&tmem_full[buf], (n >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BNT; c0 += 32, ++chunk) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)TCOLS + (uint32_t)c0, v);
+                if (c0 + 32 >= BNT) {
+                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                const int gj0 = j0 + c0;
+                const int ncol = min(32, min(BNT - c0, e.J - gj0));
+                uint8_t* cbuf = stage_c + (chunk & 1) * SLOT;
+                uint8_t* pbuf = stage_p + (chunk & 1) * SLOT;
+                // the staging slot was last used two chunks ago: its TMA store must have finished reading it
+                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // (also publishes the bias tile on the first chunk)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float x[4] = {v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]};
+                    if (use_bias) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * u);
+                        x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+                    }
+                    const uint32_t soff = (uint32_t)row * 128u + ((uint32_t)(u ^ (row & 7)) << 4);
+                    if (EPI == 1) {
+                        if (want_pre) *reinterpret_cast<float4*>(pbuf + soff) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) x[w] = gelu_erf(x[w]);
+                    }
+                    if (EPI == 3) {
+                        x[0] *= gelu_erf_grad(av[u].x); x[1] *= gelu_erf_grad(av[u].y);
+                        x[2] *= gelu_erf_grad(av[u].z); x[3] *= gelu_erf_grad(av[u].w);
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) x[w] *= rs;
+                    if (EPI == 2) { x[0] += av[u].x; x[1] += av[u].y; x[2] += av[u].z; x[3] += av[u].w; }
+                    *reinterpret_cast<float4*>(cbuf + soff) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+                if (c0 + 32 < BNT) load_aux(c0 + 32, av);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (elected) {
+                    if (ncol > 0) {
+                        if (EPI == 4 || EPI == 5) tma_reduce_add_2d(&mapC, cbuf, gj0, i0);
+                        else tma_store_2d(&mapC, cbuf, gj0, i0);
+                        if (want_pre) tma_store_2d(&mapP, pbuf, gj0, i0);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TCOLS));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -491,14 +792,55 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
     e.kb_total = (R + TKB - 1) / TKB;
     e.kb_per_split = (kb_per_split > 0 && kb_per_split < e.kb_total) ? kb_per_split : e.kb_total;
     const int splits = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
-    const size_t smem = 1024 + (size_t)(e.split3 ? 12 : 6) * (TM * TKB * 4) + 256;
+    const size_t smem = 1024 + (size_t)(e.split3 ? 12 : 6) * (TM * TKB * 4) + 256 + 512;   // ring + barriers + bias tile
     dim3 grid((I + TM - 1) / TM, (J + BNT - 1) / BNT, splits);
+    // several tiles per SM: persistent kernel (epilogue of tile n overlaps the main loop of tile n+1)
+    static const bool no_persist = getenv("MICFORMER_GEMM_ONESHOT") != nullptr;
+    const int64_t ntiles = (int64_t)grid.x * grid.y * grid.z;
+    if (!no_persist && ntiles >= 2 * (int64_t)num_sms() && ntiles < (1 << 30)) {
+        TcpSched sc{};
+        sc.tiles_i = (int)grid.x; sc.tiles_j = (int)grid.y; sc.splits = splits; sc.ntiles = (int)ntiles;
+        sc.stage_slots = e.split3 ? 4 : 2;
+        const int stage_bytes = sc.stage_slots * TM * TKB * 4;
+        const int staging = ((epi == 1 && e.pre) ? 4 : 2) * TM * TKB * 4;
+        int nst = (int)((227 * 1024 - 1024 - 2048 - staging) / stage_bytes);
+        if (nst > 6) nst = 6;
+        if (nst > e.kb_per_split * 2) nst = e.kb_per_split * 2 > 2 ? e.kb_per_split * 2 : 2;
+        sc.nst = nst;
+        const size_t psmem = 1024 + (size_t)nst * stage_bytes + staging + 256 + 1024 + 256;
+        const int pgrid = num_sms();
+#define PLAUNCH(AM, BM_, EP)                                                                                         \
+    do {                                                                                                             \
+        static size_t attr_sz = 0;                                                                                   \
+        if (attr_sz < psmem) {                                                                                       \
+            cudaFuncSetAttribute(gemm_tcp_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            attr_sz = 227 * 1024;                                                                                    \
+        }                                                                                                            \
+        gemm_tcp_kernel<AM, BM_, EP><<<pgrid, TCP_THREADS, psmem, st>>>(mA, mB, mC, mP, e, sc, BNT, TCOLS);            \
+    } while (0)
+#define PLAUNCH_EPI(AM, BM_)                                                           \
+    switch (epi) {                                                                     \
+        case 0: PLAUNCH(AM, BM_, 0); break;                                            \
+        case 1: PLAUNCH(AM, BM_, 1); break;                                            \
+        case 2: PLAUNCH(AM, BM_, 2); break;                                            \
+        case 3: PLAUNCH(AM, BM_, 3); break;                                            \
+        case 4: PLAUNCH(AM, BM_, 4); break;                                            \
+        default: PLAUNCH(AM, BM_, 5); break;                                           \
+    }
+        if (!A.mn_major && !B.mn_major) { PLAUNCH_EPI(false, false) }
+        else if (!A.mn_major && B.mn_major) { PLAUNCH_EPI(false, true) }
+        else if (A.mn_major && B.mn_major) { PLAUNCH(true, true, 5); }
+        else return MIC_ERR_UNSUPPORTED;
+#undef PLAUNCH_EPI
+#undef PLAUNCH
+        return check_launch("gemm_tcp_kernel");
+    }
 #define LAUNCH(AM, BM_, EP)                                                                                      \
     do {                                                                                                         \
         static bool attr_done = false;                                                                           \
         if (!attr_done) {                                                                                        \
             cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                 (int)(1024 + 12 * TM * TKB * 4 + 256));                                         \
+                                 (int)(1024 + 12 * TM * TKB * 4 + 256 + 512));                                         \
             attr_done = true;                                                                                    \
         }                                                                                                        \
         gemm_tc_kernel<AM, BM_, EP><<<grid, TC_THREADS, smem, st>>>(mA, mB, mC, mP, e, BNT, TCOLS);                       \
@@ -542,8 +884,11 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
     // (the MMAs are not the bottleneck of these HBM/latency-bound shapes); MICFORMER_TF32_FWD=1 selects single-pass
     // nearest-rounded TF32 (measured 8e-4..1e-3 logits error at 64^3/128^3)
     static const int fwd_single = []() { const char* v = getenv("MICFORMER_TF32_FWD"); return v && v[0] == '1'; }();
+    // MICFORMER_TF32_FWD_SMALL_M=<rows>: GEMMs with at most that many rows (the deep, latency-bound stages) run
+    // single-pass nearest-rounded TF32; the large-M stages and the decoder tail keep the 3xTF32 split
+    static const int small_m = []() { const char* v = getenv("MICFORMER_TF32_FWD_SMALL_M"); return v ? atoi(v) : 0; }();
     e.round_rn = 1;
-    e.split3 = fwd_single ? 0 : 1;
+    e.split3 = (fwd_single || M <= small_m) ? 0 : 1;
     TcOperand A{X, false, ldx};
     TcOperand B{W, w_is_kn != 0, ldw};      // W[n,k]: K-major; W[k,n]: MN-major
     return tc_gemm(A, B, e, K, 0, st);

@@ -12,6 +12,7 @@
 // TMEM: S/P 352 columns + O 32 columns.  Scores never touch shared or global memory.  fp32 in / fp32 out, operands
 // read as TF32, fp32 accumulation (the HBM floor with fp32 I/O is above the TF32 tensor time).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mic {
@@ -62,6 +63,14 @@ __device__ __forceinline__ void abar_wait(uint64_t* b, uint32_t parity) {
         "bra AW_LOOP;\n"
         "AW_DONE:\n"
         "}\n" ::"r"(asmem(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool abar_test(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(asmem(b)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void acommit(uint64_t* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(asmem(b)) : "memory");
@@ -379,6 +388,355 @@ window_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2: two softmax pipelines per CTA.  v1 serialises  S-MMA -> softmax -> PV-MMA  per 128-row tile because one fp32 S
+// tile (352 columns) nearly fills TMEM; the SFU (ex2) then idles during the MMAs and the tensor core during the
+// softmax.  Here the keys are split into two blocks (192 | N-192) handled with a two-block online softmax whose
+// partial outputs O0 / O1 are kept in separate accumulators and merged in the epilogue (out = (O0*alpha + O1) / l),
+// so one tile needs only 192 + 2*32 = 256 TMEM columns and TWO tiles are in flight: while pipeline A's four warps
+// exponentiate a block, the tensor core runs pipeline B's QK^T / PV, and vice versa.
+//   warp 0       TMA producer (as v1)
+//   warp 1       MMA issuer for both pipelines (fixed interleave A/B)
+//   warps 2-5    softmax + epilogue, pipeline A (even tiles)
+//   warps 6-9    softmax + epilogue, pipeline B (odd tiles)
+//   warps 10-11  operand conditioning: round Q/K/V to nearest TF32 in shared memory (off the softmax warps' path)
+constexpr int A2_THREADS = 384;            // 12 warps -> 168 registers per thread
+constexpr int A2_B0 = 192;                      // keys in block 0 (6 x 32-column chunks)
+constexpr int A2_PIPE_COLS = 256;               // S/P 192 + O0 32 + O1 32
+
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m, int valid) {
+    float m0 = m, m1 = m, m2 = m, m3 = m;                  // four chains instead of one 32-deep dependency
+    if (valid >= 32) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[t])); m1 = fmaxf(m1, __uint_as_float(v[t + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[t + 2])); m3 = fmaxf(m3, __uint_as_float(v[t + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) if (t < valid) m0 = fmaxf(m0, __uint_as_float(v[t]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// v <- RN_tf32(exp2(v * sc - mb)) (0 beyond `valid`); returns the sum of the rounded values
+__device__ __forceinline__ float chunk_exp(uint32_t (&v)[32], float sc, float mb, int valid) {
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        float p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(__uint_as_float(v[t]), sc, -mb)));
+        if (valid < 32 && t >= valid) p = 0.f;
+        const uint32_t pr = (__float_as_uint(p) + 0x1000u) & 0xFFFFE000u;
+        if ((t & 3) == 0) l0 += __uint_as_float(pr);
+        else if ((t & 3) == 1) l1 += __uint_as_float(pr);
+        else if ((t & 3) == 2) l2 += __uint_as_float(pr);
+        else l3 += __uint_as_float(pr);
+        v[t] = pr;
+    }
+    return (l0 + l1) + (l2 + l3);
+}
+
+// One key block of the two-block softmax for this thread's row: S (nch 32-column chunks at taddr, `valid` real columns)
+// -> m = max(m_in, row max), P = RN_tf32(exp2((S - m) * sc)) written in place, l = sum(P).  The max pass streams the
+// chunks through va (even) / vb (odd); the last two chunks are still in registers when the exp pass starts, so only
+// nch - 2 chunks are read from TMEM twice (TMEM reads are the scarcest port of this kernel).
+__device__ __forceinline__ void softmax_block(uint32_t taddr, int nch, int valid, float m_in, float sc, float& m_out,
+                                              float& l_out, uint32_t (&va)[32], uint32_t (&vb)[32]) {
+    float m = m_in;
+    tld32_nowait(taddr, va);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c = 0; c < nch; c += 2) {
+        if (c + 1 < nch) tld32_nowait(taddr + (uint32_t)((c + 1) * 32), vb);
+        m = chunk_max(va, m, valid - c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 1 < nch) {
+            if (c + 2 < nch) tld32_nowait(taddr + (uint32_t)((c + 2) * 32), va);
+            m = chunk_max(vb, m, valid - (c + 1) * 32);
+            if (c + 2 < nch) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+    }
+    const float mb = m * sc;
+    float l = 0.f;
+    const int L = nch - 1;                            // va holds the last even chunk, vb the last odd one
+    if (L & 1) {
+        l += chunk_exp(vb, sc, mb, valid - L * 32);
+        tst32(taddr + (uint32_t)(L * 32), vb);
+        l += chunk_exp(va, sc, mb, valid - (L - 1) * 32);
+        tst32(taddr + (uint32_t)((L - 1) * 32), va);
+    } else {
+        l += chunk_exp(va, sc, mb, valid - L * 32);
+        tst32(taddr + (uint32_t)(L * 32), va);
+        if (L >= 1) {
+            l += chunk_exp(vb, sc, mb, valid - (L - 1) * 32);
+            tst32(taddr + (uint32_t)((L - 1) * 32), vb);
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const int nrem = L - 1;                           // chunks [0, nrem) are read again
+    if (nrem > 0) {
+        tld32_nowait(taddr, va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c = 0; c < nrem; c += 2) {
+            if (c + 1 < nrem) tld32_nowait(taddr + (uint32_t)((c + 1) * 32), vb);
+            l += chunk_exp(va, sc, mb, 32);
+            tst32(taddr + (uint32_t)(c * 32), va);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (c + 1 < nrem) {
+                if (c + 2 < nrem) tld32_nowait(taddr + (uint32_t)((c + 2) * 32), va);
+                l += chunk_exp(vb, sc, mb, 32);
+                tst32(taddr + (uint32_t)((c + 1) * 32), vb);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+        }
+    }
+    m_out = m;
+    l_out = l;
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapV, AttnTcArgs a) {
+    extern __shared__ uint8_t at_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = sm;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + AT_SLOTS * AT_SLOT_BYTES + 4096);   // +4 KB: Q tile over-read pad
+    uint64_t* empty = full + AT_SLOTS;
+    uint64_t* rdy = empty + AT_SLOTS;          // slot rounded to TF32 (64 arrivals)
+    uint64_t* s_full = rdy + AT_SLOTS;         // [2]
+    uint64_t* p_full = s_full + 2;             // [2] 128 arrivals
+    uint64_t* o_full = p_full + 2;             // [2]
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmt = (a.N + 127) / 128;
+    const uint32_t box_bytes = (uint32_t)a.N * 128u;
+    const int64_t nit = (a.items - blockIdx.x + gridDim.x - 1) / gridDim.x;     // items of this CTA
+    const int64_t G = nit * nmt;                                                 // tiles of this CTA
+    const int w1 = a.Nk - A2_B0;               // key columns of block 1 (multiple of 32)
+    const int v1 = a.N - A2_B0;                // valid ones
+
+    for (int i = threadIdx.x; i < (AT_SLOTS * AT_SLOT_BYTES + 4096) / 16; i += A2_THREADS)
+        reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AT_SLOTS; ++s) { abar_init(&full[s], 1); abar_init(&empty[s], 1); abar_init(&rdy[s], 64); }
+        for (int x = 0; x < 2; ++x) { abar_init(&s_full[x], 1); abar_init(&p_full[x], 128); abar_init(&o_full[x], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(asmem(tslot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQK) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+            int64_t u = 0;
+            for (int64_t it = blockIdx.x; it < a.items; it += gridDim.x) {
+                const int head = (int)(it % a.heads);
+                int64_t w = it / a.heads;
+                const int wx = (int)(w % a.nww); w /= a.nww;
+                const int wy = (int)(w % a.nwh); w /= a.nwh;
+                const int wz = (int)(w % a.nwd); w /= a.nwd;
+                const int b = (int)w;
+#pragma unroll
+                for (int part = 0; part < 3; ++part, ++u) {        // 0: Q, 1: K, 2: V
+                    const int s = (int)(u % AT_SLOTS);
+                    abar_wait(&empty[s], (uint32_t)((u / AT_SLOTS) & 1) ^ 1u);
+                    abar_expect(&full[s], box_bytes);
+                    tma_load_5d(ring + s * AT_SLOT_BYTES, part == 2 ? &mapV : &mapQK, &full[s], part * a.C + head * 32,
+                                wx * a.ww, wy * a.wh, wz * a.wd, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(A2_B0 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_s1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(w1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) |
+                                     ((uint32_t)(128 >> 4) << 24);
+            const int ks_pv1 = (v1 + 7) / 8;
+            uint32_t pw[2] = {0u, 0u};                  // p_full phases consumed per pipeline
+            const uint32_t ring_a = asmem(ring);
+            auto slot_addr = [&](int u) { return ring_a + (uint32_t)(u % AT_SLOTS) * AT_SLOT_BYTES; };
+            auto issue_s = [&](int x, int j, int mt, int h) {
+                const uint32_t qa = slot_addr(3 * j), ka = slot_addr(3 * j + 1);
+                const uint32_t d = tmem + (uint32_t)(x * A2_PIPE_COLS);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = adesc(qa + (uint32_t)(mt * 128 * 128 + ks * 32), 16, 1024, 2);
+                    const uint64_t bd = adesc(ka + (uint32_t)(h * A2_B0 * 128 + ks * 32), 16, 1024, 2);
+                    amma_ss(d, ad, bd, h ? idesc_s1 : idesc_s0, ks ? 1u : 0u);
+                }
+                acommit(&s_full[x]);
+            };
+            auto issue_pv = [&](int x, int j, int h) {
+                const uint32_t va = slot_addr(3 * j + 2);
+                const uint32_t pcol = tmem + (uint32_t)(x * A2_PIPE_COLS);
+                const uint32_t ocol = pcol + (uint32_t)(A2_B0 + 32 * h);
+                const int n = h ? ks_pv1 : A2_B0 / 8;
+                uint64_t bd = adesc(va + (uint32_t)(h * (A2_B0 / 8) * 1024), 4096, 512, 1);
+                for (int kk = 0; kk < n; ++kk, bd += 1024 >> 4)      // next 8 key rows: start address + 1 KB
+                    amma_ts(ocol, pcol + (uint32_t)(kk * 8), bd, idesc_o, kk ? 1u : 0u);
+            };
+            // Each pipeline x walks its tiles g = x, x+2, ... through three issue steps; the issuer polls both pipelines
+            // and issues whichever step has its inputs ready (a pipeline waiting for the next item's V does not stall
+            // the other one):
+            //   step 0: S(block 0)                       needs Q, K of the item rounded (first tile of the item)
+            //   step 1: PV(block 0) -> O0, S(block 1)    needs P(block 0) published [+ V rounded]
+            //   step 2: PV(block 1) -> O1                needs P(block 1) published
+            // Q/K (V) slots are released when all nmt tiles of the item have issued step 1 (step 2).
+            int jx[2] = {0, 1 / nmt}, mx[2] = {0, 1 % nmt};   // (item, tile) of each pipeline's current tile: tile index g = x, x+2, ..
+            int64_t gx[2] = {0, 1};
+            int st[2] = {0, 0};
+            int done1[2] = {0, 0}, done2[2] = {0, 0};   // per item parity (j & 1): tiles that issued step 1 / step 2
+            int live = (G > 0) + (G > 1);
+            if (G <= 1) st[1] = 3;
+            if (G <= 0) st[0] = 3;
+            while (live > 0) {
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    if (st[x] == 3) continue;
+                    const int j = jx[x], mt = mx[x];
+                    const int u0 = 3 * j;               // slot-use index of this item's Q (K = +1, V = +2)
+                    if (st[x] == 0) {
+                        // (re-testing a completed phase is cheap; the slot cannot be re-armed while this item is live)
+                        if (!abar_test(&rdy[u0 % AT_SLOTS], (uint32_t)((u0 / AT_SLOTS) & 1))) continue;
+                        if (!abar_test(&rdy[(u0 + 1) % AT_SLOTS], (uint32_t)(((u0 + 1) / AT_SLOTS) & 1))) continue;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_s(x, j, mt, 0);
+                        st[x] = 1;
+                    } else if (st[x] == 1) {
+                        if (!abar_test(&p_full[x], pw[x] & 1u)) continue;
+                        if (!abar_test(&rdy[(u0 + 2) % AT_SLOTS], (uint32_t)(((u0 + 2) / AT_SLOTS) & 1))) continue;
+                        ++pw[x];
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_pv(x, j, 0);
+                        issue_s(x, j, mt, 1);
+                        if (++done1[j & 1] == nmt) {
+                            done1[j & 1] = 0;
+                            acommit(&empty[u0 % AT_SLOTS]); acommit(&empty[(u0 + 1) % AT_SLOTS]);
+                        }
+                        st[x] = 2;
+                    } else {
+                        if (!abar_test(&p_full[x], pw[x] & 1u)) continue;
+                        ++pw[x];
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_pv(x, j, 1);
+                        acommit(&o_full[x]);
+                        if (++done2[j & 1] == nmt) {
+                            done2[j & 1] = 0;
+                            acommit(&empty[(u0 + 2) % AT_SLOTS]);
+                        }
+                        gx[x] += 2;
+                        mx[x] += 2;
+                        if (mx[x] >= nmt) { mx[x] -= nmt; ++jx[x]; }     // nmt >= 2: at most one wrap
+                        st[x] = 0;
+                        if (gx[x] >= G) { st[x] = 3; --live; }
+                    }
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ------------------------------------------------------------------ softmax + epilogue, pipeline x
+        const int x = warp >= 6 ? 1 : 0;
+        const int q = warp & 3;                       // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;                  // query row inside the 128-row tile
+        const uint32_t sbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * A2_PIPE_COLS);
+        const int nch1 = w1 / 32;
+        uint32_t va[32], vb[32];
+        // token offset inside the window for this thread's row of each M-tile (nmt <= 3), computed once
+        int64_t tokoff[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int i = t * 128 + r;
+            const int ix = i % a.ww, iy = (i / a.ww) % a.wh, iz = i / (a.ww * a.wh);
+            tokoff[t] = i < a.N ? ((int64_t)iz * a.Hp + iy) * a.Wp + ix : -1;
+        }
+        uint32_t un = 0;                              // tiles done by this pipeline
+        int j = 0, mt = x;                            // nmt >= 2: tile g = x is (item 0, tile x)
+        for (int64_t g = x; g < G; g += 2, ++un) {
+            const uint32_t it = blockIdx.x + (uint32_t)j * gridDim.x;
+            // ---- block 0: keys [0, 192), all valid
+            abar_wait(&s_full[x], 0u);                // two s_full phases per tile: parities 0, 1
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float m0, l0;
+            softmax_block(sbase, A2_B0 / 32, A2_B0, -INFINITY, a.scale_log2, m0, l0, va, vb);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            abar_arrive(&p_full[x]);
+            // ---- block 1: keys [192, N)
+            abar_wait(&s_full[x], 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float m1, l1;
+            softmax_block(sbase, nch1, v1, m0, a.scale_log2, m1, l1, va, vb);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            abar_arrive(&p_full[x]);
+            const float mb0 = m0 * a.scale_log2, mb1 = m1 * a.scale_log2;
+            // ---- epilogue: out = (O0 * alpha + O1) / (l0 * alpha + l1), alpha = 2^((m0 - m1) * scale * log2 e)
+            float alpha;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(mb0 - mb1));
+            const float l = fmaf(l0, alpha, l1);
+            abar_wait(&o_full[x], (uint32_t)(un & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tld32_nowait(sbase + A2_B0, va);
+            tld32_nowait(sbase + A2_B0 + 32, vb);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int64_t toff = mt == 0 ? tokoff[0] : (mt == 1 ? tokoff[1] : tokoff[2]);
+            if (toff >= 0) {
+                const uint32_t head = it % (uint32_t)a.heads;
+                uint32_t w = it / (uint32_t)a.heads;
+                const uint32_t wx = w % (uint32_t)a.nww; w /= (uint32_t)a.nww;
+                const uint32_t wy = w % (uint32_t)a.nwh; w /= (uint32_t)a.nwh;
+                const uint32_t wz = w % (uint32_t)a.nwd; w /= (uint32_t)a.nwd;   // w = batch index
+                const int64_t row = (((int64_t)w * a.Dp + wz * a.wd) * a.Hp + wy * a.wh) * a.Wp + wx * a.ww + toff;
+                const float inv = 1.f / l;
+                const float ai = alpha * inv;
+                float* dst = a.out + row * a.ldo + head * 32;
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    *reinterpret_cast<float4*>(dst + 4 * t) =
+                        make_float4(fmaf(__uint_as_float(va[4 * t]), ai, __uint_as_float(vb[4 * t]) * inv),
+                                    fmaf(__uint_as_float(va[4 * t + 1]), ai, __uint_as_float(vb[4 * t + 1]) * inv),
+                                    fmaf(__uint_as_float(va[4 * t + 2]), ai, __uint_as_float(vb[4 * t + 2]) * inv),
+                                    fmaf(__uint_as_float(va[4 * t + 3]), ai, __uint_as_float(vb[4 * t + 3]) * inv));
+                a.lse[row * a.heads + head] = fmaf(__log2f(l), 0.6931471805599453f, m1 * a.scale);
+            }
+            mt += 2;
+            if (mt >= nmt) { mt -= nmt; ++j; }
+        }
+    } else {
+        // ------------------------------------------------------------------ operand conditioning (warps 10-11)
+        const int et = (warp - 10) * 32 + lane;      // 0..63
+        const int nvec = a.N * 8;                     // float4 per operand tile
+        for (int64_t u = 0; u < 3 * nit; ++u) {
+            const int s = (int)(u % AT_SLOTS);
+            abar_wait(&full[s], (uint32_t)((u / AT_SLOTS) & 1));
+            uint4* p4 = reinterpret_cast<uint4*>(ring + s * AT_SLOT_BYTES);
+#pragma unroll 8
+            for (int i = et; i < nvec; i += 64) {
+                uint4 t = p4[i];
+                t.x = (t.x + 0x1000u) & 0xFFFFE000u; t.y = (t.y + 0x1000u) & 0xFFFFE000u;
+                t.z = (t.z + 0x1000u) & 0xFFFFE000u; t.w = (t.w + 0x1000u) & 0xFFFFE000u;
+                p4[i] = t;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            abar_arrive(&rdy[s]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -430,6 +788,16 @@ int tc_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, 
     }
     int64_t grid = num_sms();
     if (grid > a.items) grid = a.items;
+    static const bool force_v1 = getenv("MICFORMER_ATTN_V1") != nullptr;
+    if (N > A2_B0 && !force_v1) {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(window_attn_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr2 = true;
+        }
+        window_attn_tc2_fwd_kernel<<<(unsigned)grid, A2_THREADS, smem, st>>>(mQK, mV, a);
+        return check_launch("window_attn_tc2_fwd_kernel");
+    }
     window_attn_tc_fwd_kernel<<<(unsigned)grid, AT_THREADS, smem, st>>>(mQK, mV, a);
     return check_launch("window_attn_tc_fwd_kernel");
 }

@@ -28,7 +28,8 @@ def _rand(*shape, seed=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 48, 32), (300, 144, 48), (1000, 192, 48), (128, 384, 1536), (517, 96, 24),
-                                   (64, 1536, 96), (8192, 96, 96), (130, 80, 40)])
+                                   (64, 1536, 96), (8192, 96, 96), (130, 80, 40),
+                                   (40000, 144, 48), (33333, 80, 200)])     # >= 2 tiles per SM: persistent kernel
 @pytest.mark.parametrize("w_is_kn", [False, True])
 def test_tc_linear_all_layouts(tc_mode, M, N, K, w_is_kn):
     from micformer_b200 import ops
@@ -47,9 +48,10 @@ def test_tc_linear_all_layouts(tc_mode, M, N, K, w_is_kn):
     assert max_rel(db.cpu(), dy.double().sum(0)) < 1e-5
 
 
-def test_tc_epilogues_and_strided_views(tc_mode):
+@pytest.mark.parametrize("M", [2048, 65536])       # one-shot kernel / persistent kernel
+def test_tc_epilogues_and_strided_views(tc_mode, M):
     from micformer_b200 import ops
-    M, N, K = 2048, 192, 48
+    N, K = 192, 48
     x = _rand(M, K, seed=1); w = _rand(N, K, seed=2) * 0.1; b = _rand(N, seed=3); res = _rand(M, N, seed=4)
     xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
     ref = x.double() @ w.double().t() + b.double()
@@ -108,7 +110,10 @@ def test_tc_whole_model_logits_within_baseline_bar(tc_mode, S):
 
 
 @pytest.mark.parametrize("B,pd,ws,C,heads", [(1, (7, 7, 7), (7, 7, 7), 96, 3), (2, (7, 14, 14), (7, 7, 7), 96, 3),
-                                             (2, (8, 8, 8), (4, 8, 8), 64, 2), (1, (14, 7, 21), (7, 7, 7), 192, 6)])
+                                             (2, (8, 8, 8), (4, 8, 8), 64, 2), (1, (14, 7, 21), (7, 7, 7), 192, 6),
+                                             (1, (8, 6, 12), (4, 6, 6), 64, 2),      # 144 tokens: single-pipeline kernel
+                                             (2, (10, 6, 7), (5, 6, 7), 32, 1),      # 210 tokens: 192 + 18 key split
+                                             (3, (21, 21, 21), (7, 7, 7), 96, 3)])   # 243 items: several per CTA
 def test_tc_window_attention_large_windows(tc_mode, B, pd, ws, C, heads):
     """tcgen05 FlashAttention-style kernel (343-token windows, head_dim 32): TMA 5-D window gather, S/P in TMEM."""
     from micformer_b200 import ops
