@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_tc.py -x -q -k "linear or epilogues" ) > gpurun_out/pytest_gemm.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gemm.log
+tail -15 gpurun_out/pytest_gemm.log
+if grep -q "rc=0" gpurun_out/pytest_gemm.log; then
+  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --dump-kernels gpurun_out/kernels_j.json > gpurun_out/bench_j.json 2> gpurun_out/bench_j.err
+  MICFORMER_GEMM_ONESHOT=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-kernel-pass 2>/dev/null | cut -c1-200 > gpurun_out/bench_j_oneshot.json
+  tail -6 gpurun_out/pytest_gpu.log; cut -c1-300 gpurun_out/bench_j.json; cat gpurun_out/bench_j_oneshot.json
+fi
