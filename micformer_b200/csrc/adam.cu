@@ -13,6 +13,7 @@ constexpr int ADAM_CHUNK = 32768;      // elements per CTA
 
 // per-tensor step counters (torch.optim.Adam keeps one per parameter and skips parameters without a gradient)
 __global__ void adam_tick_kernel(float* __restrict__ steps, const float* const* __restrict__ grads, int n_tensors) {
+    pdl_sync();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_tensors && grads[t] != nullptr) steps[t] += 1.f;
 }
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* const* __restrict__ pa
                                                    const int* __restrict__ chunk_index, const float* __restrict__ steps,
                                                    const float* __restrict__ lr_dev, float beta1, float beta2, float eps,
                                                    float weight_decay) {
+    pdl_sync();
     const int t = chunk_tensor[blockIdx.x];
     const int64_t off = (int64_t)chunk_index[blockIdx.x] * ADAM_CHUNK;
     const int64_t n = min((int64_t)ADAM_CHUNK, sizes[t] - off);
@@ -85,10 +87,10 @@ extern "C" int mic_adam_step(void* params, void* grads, void* exp_avg, void* exp
     MIC_REQUIRE(params && grads && exp_avg && exp_avg_sq && sizes && chunk_tensor && chunk_index && steps && lr &&
                     n_chunks > 0 && n_tensors > 0, "adam_step: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    adam_tick_kernel<<<(n_tensors + 255) / 256, 256, 0, st>>>(steps, reinterpret_cast<const float* const*>(grads), n_tensors);
+    mic::launch(adam_tick_kernel, dim3((n_tensors + 255) / 256), dim3(256), 0, st, steps, reinterpret_cast<const float* const*>(grads), n_tensors);
     int rc = check_launch("adam_tick_kernel");
     if (rc) return rc;
-    adam_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<float* const*>(params), reinterpret_cast<const float* const*>(grads),
+    mic::launch(adam_kernel, dim3(n_chunks), dim3(256), 0, st, reinterpret_cast<float* const*>(params), reinterpret_cast<const float* const*>(grads),
                                           reinterpret_cast<float* const*>(exp_avg), reinterpret_cast<float* const*>(exp_avg_sq),
                                           sizes, chunk_tensor, chunk_index, steps, lr, beta1, beta2, eps, weight_decay);
     return check_launch("adam_kernel");

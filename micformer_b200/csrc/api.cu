@@ -2,6 +2,7 @@
 // exact fp32 CUDA-core kernels and the tcgen05 tensor-core kernels.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mic {
@@ -45,6 +46,13 @@ int simt_window_attn_bwd(const float*, int, const float*, const float*, int, con
 }  // namespace mic
 
 using namespace mic;
+
+namespace mic {
+bool pdl_enabled() {
+    static const bool on = []() { const char* v = getenv("MICFORMER_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+}  // namespace mic
 
 extern "C" int mic_version(void) { return 100; }
 extern "C" const char* mic_last_error_string(void) { return g_err; }

@@ -52,6 +52,32 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- programmatic dependent launch (PDL).  Every kernel is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_sync(): griddepcontrol.wait blocks until the preceding kernel of the stream has
+// completed and flushed (so all reads/writes below it are ordered exactly as without PDL), then launch_dependents lets
+// the NEXT kernel's CTAs be scheduled and run their prologue (barrier init, TMEM allocation, descriptor prefetch, index
+// math) while this kernel works.  The chains of 5-10 us kernels of the deep stages overlap launch latency + prologue.
+// MICFORMER_PDL=0 disables the attribute (griddepcontrol is then a no-op).
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(128) conv3_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ Wt, const float* __restrict__ bias,
                                                         float* __restrict__ y, ConvGeom g, int out_ncdhw,
                                                         int units_per_split) {
+    pdl_sync();
     constexpr int OG = COP / 4;          // output groups of 4
     constexpr int PG = 128 / OG;         // position groups
     constexpr int TP = PG * 4;           // positions per CTA
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) conv3_bwd_data_kernel(const float* __rest
                                                              float* __restrict__ dx0, int acc0,
                                                              float* __restrict__ dx1, int acc1, ConvGeom g,
                                                              int dy_ncdhw) {
+    pdl_sync();
     constexpr int TP = 128, TC = 32;
     __shared__ __align__(16) float As[COP][TP + 4];   // dy^T : [o][pos]
     __shared__ __align__(16) float Ws[COP][TC + 4];   // [o][c]
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(32 * (COP / 4)) conv3_bwd_weight_kernel(const 
                                                                          float* __restrict__ dWt,
                                                                          float* __restrict__ dbias, ConvGeom g,
                                                                          int dy_ncdhw, int nbz, int nby, int nbx) {
+    pdl_sync();
     constexpr int NT = 32 * (COP / 4);
     extern __shared__ __align__(16) float smem[];
     float* Xs = smem;                   // [NH][33]
@@ -349,8 +352,8 @@ extern "C" int mic_conv3_fwd(const float* x0, int C0, const float* x1, int C1, c
         if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "conv3_fwd memset: %s", cudaGetErrorString(e));
     }
     dim3 grid((unsigned)tiles, splits);
-    if (Co <= 8) conv3_fwd_kernel<8><<<grid, 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw, ups);
-    else conv3_fwd_kernel<16><<<grid, 128, 0, st>>>(x0, x1, Wt, bias, y, g, out_ncdhw, ups);
+    if (Co <= 8) mic::launch((conv3_fwd_kernel<8>), grid, dim3(128), 0, st, x0, x1, Wt, bias, y, g, out_ncdhw, ups);
+    else mic::launch((conv3_fwd_kernel<16>), grid, dim3(128), 0, st, x0, x1, Wt, bias, y, g, out_ncdhw, ups);
     return check_launch("conv3_fwd_kernel");
 }
 
@@ -364,8 +367,8 @@ extern "C" int mic_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, 
     const int64_t Q = (int64_t)B * D * H * W;
     dim3 grid((unsigned)ceil_div64(Q, 128), ceil_div(C0 + C1, 32));
     cudaStream_t st = (cudaStream_t)stream;
-    if (Co <= 8) conv3_bwd_data_kernel<8><<<grid, 256, 0, st>>>(dy, Wt, dx0, acc0, dx1, acc1, g, dy_ncdhw);
-    else conv3_bwd_data_kernel<16><<<grid, 256, 0, st>>>(dy, Wt, dx0, acc0, dx1, acc1, g, dy_ncdhw);
+    if (Co <= 8) mic::launch((conv3_bwd_data_kernel<8>), grid, dim3(256), 0, st, dy, Wt, dx0, acc0, dx1, acc1, g, dy_ncdhw);
+    else mic::launch((conv3_bwd_data_kernel<16>), grid, dim3(256), 0, st, dy, Wt, dx0, acc0, dx1, acc1, g, dy_ncdhw);
     return check_launch("conv3_bwd_data_kernel");
 }
 
@@ -388,12 +391,12 @@ extern "C" int mic_conv3_bwd_weight(const float* dy, const float* x0, int C0, co
         const size_t smem = (NH * 33 + NB * 8) * sizeof(float);
         static bool once8 = false;
         if (!once8) { cudaFuncSetAttribute(conv3_bwd_weight_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once8 = true; }
-        conv3_bwd_weight_kernel<8><<<grid, 64, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_bwd_weight_kernel<8>), grid, dim3(64), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     } else {
         const size_t smem = (NH * 33 + NB * 16) * sizeof(float);
         static bool once16 = false;
         if (!once16) { cudaFuncSetAttribute(conv3_bwd_weight_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once16 = true; }
-        conv3_bwd_weight_kernel<16><<<grid, 128, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_bwd_weight_kernel<16>), grid, dim3(128), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     }
     return check_launch("conv3_bwd_weight_kernel");
 }

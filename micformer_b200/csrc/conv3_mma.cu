@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(M_THREADS, 2)
 conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x0, const float* __restrict__ x1,
                             float* __restrict__ dWt, float* __restrict__ dbias, MGeom g, int dy_ncdhw, int nbz, int nby,
                             int nbx) {
+    pdl_sync();
     constexpr int NTN = COP / 8;
     extern __shared__ __align__(16) float msm[];
     float* Xs = msm;                        // [M_NH][XS]
@@ -222,11 +223,11 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
     if (Co == 8) {
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(conv3_mma_bwd_weight_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-        conv3_mma_bwd_weight_kernel<8><<<grid, M_THREADS, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_mma_bwd_weight_kernel<8>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     } else {
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(conv3_mma_bwd_weight_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-        conv3_mma_bwd_weight_kernel<16><<<grid, M_THREADS, smem, st>>>(dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_mma_bwd_weight_kernel<16>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
     }
     return check_launch("conv3_mma_bwd_weight_kernel");
 }

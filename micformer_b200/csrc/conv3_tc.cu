@@ -147,6 +147,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
+    pdl_sync();            // prologue above (barriers, TMEM) overlaps the previous kernel
 
     if (warp < 4) {
         // ------------------------------------------------------------------ producers
@@ -387,7 +388,7 @@ static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, c
         if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "%s memset: %s", who, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)((int64_t)foot * g.nseg), (unsigned)nych, (unsigned)g.ksplit);
-    conv3_tc_kernel<NT><<<grid, CT_THREADS, smem, st>>>(x0, x1, Wsrc, bias, y0, y1, g, tcols);
+    mic::launch((conv3_tc_kernel<NT>), grid, dim3(CT_THREADS), smem, st, x0, x1, Wsrc, bias, y0, y1, g, tcols);
     return check_launch(who);
 }
 

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) offset_head_fwd_kernel(const float* __res
                                                               const float* __restrict__ beta,
                                                               const float* __restrict__ w3, float* __restrict__ pos,
                                                               int64_t P, int Dp, int Hp, int Wp, float eps) {
+    pdl_sync();
     __shared__ float sg[HC], sb[HC], sw[3 * HC];
     if (threadIdx.x < HC) { sg[threadIdx.x] = gamma[threadIdx.x]; sb[threadIdx.x] = beta[threadIdx.x]; }
     if (threadIdx.x < 3 * HC) sw[threadIdx.x] = w3[threadIdx.x];
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) offset_head_bwd_kernel(const float* __res
                                                               const float* __restrict__ w3, float* __restrict__ dh,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ dw3, int64_t P, float eps) {
+    pdl_sync();
     __shared__ float sg[HC], sb[HC], sw[3 * HC];
     __shared__ float red[5 * HC];   // dgamma | dbeta | dw3[3][HC]
     if (threadIdx.x < HC) { sg[threadIdx.x] = gamma[threadIdx.x]; sb[threadIdx.x] = beta[threadIdx.x]; }
@@ -149,6 +151,7 @@ __device__ __forceinline__ float sample_coord(int idx, float off, int S) {
 __global__ void __launch_bounds__(256) deform_sample_fwd_kernel(const float* __restrict__ src,
                                                                 const float* __restrict__ pos,
                                                                 float* __restrict__ out, SampGeom g, int64_t total) {
+    pdl_sync();
     const int C4 = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256) deform_sample_bwd_kernel(const float* __r
                                                                 const float* __restrict__ pos,
                                                                 float* __restrict__ dsrc, float* __restrict__ dpos,
                                                                 SampGeom g, int64_t total) {
+    pdl_sync();
     const int C4 = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -240,7 +244,7 @@ extern "C" int mic_offset_head_fwd(const float* h, const float* gamma, const flo
     MIC_REQUIRE(h && gamma && beta && w3 && pos, "offset_head_fwd: null pointer");
     if (hc != HC) return fail(MIC_ERR_UNSUPPORTED, "offset_head: hidden_channels=%d (only 16 is built)", hc);
     const int64_t P = (int64_t)B * Dp * Hp * Wp;
-    offset_head_fwd_kernel<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(h, gamma, beta, w3, pos, P, Dp, Hp, Wp, eps);
+    mic::launch(offset_head_fwd_kernel, dim3(grid_for(P, 256)), dim3(256), 0, (cudaStream_t)stream, h, gamma, beta, w3, pos, P, Dp, Hp, Wp, eps);
     return check_launch("offset_head_fwd_kernel");
 }
 
@@ -253,7 +257,7 @@ extern "C" int mic_offset_head_bwd(const float* dpos, const float* h, const floa
     int64_t blocks = ceil_div64(P, 256);
     const int64_t cap = (int64_t)num_sms() * 2;
     if (blocks > cap) blocks = cap;
-    offset_head_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dpos, h, gamma, beta, w3, dh, dgamma, dbeta,
+    mic::launch(offset_head_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dpos, h, gamma, beta, w3, dh, dgamma, dbeta,
                                                                              dw3, P, eps);
     return check_launch("offset_head_bwd_kernel");
 }
@@ -265,7 +269,7 @@ extern "C" int mic_deform_sample_fwd(const float* src, const float* pos, float* 
     MIC_REQUIRE(Dp >= D && Hp >= H && Wp >= W, "deform_sample_fwd: bad geometry");
     SampGeom g{B, D, H, W, Dp, Hp, Wp, C};
     const int64_t total = (int64_t)B * Dp * Hp * Wp * (C / 4);
-    deform_sample_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, pos, out, g, total);
+    mic::launch(deform_sample_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, pos, out, g, total);
     return check_launch("deform_sample_fwd_kernel");
 }
 
@@ -278,6 +282,6 @@ extern "C" int mic_deform_sample_bwd(const float* dout, const float* src, const 
     cudaError_t e = cudaMemsetAsync(dpos, 0, P * 3 * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "deform_sample_bwd memset: %s", cudaGetErrorString(e));
     const int64_t total = P * (C / 4);
-    deform_sample_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dout, src, pos, dsrc, dpos, g, total);
+    mic::launch(deform_sample_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dout, src, pos, dsrc, dpos, g, total);
     return check_launch("deform_sample_bwd_kernel");
 }

@@ -29,6 +29,7 @@ struct GemmArgs {
 
 template <bool A_RC, bool B_RC>
 __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs p) {
+    pdl_sync();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs p) {
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N,
                                                      const float* __restrict__ rowscale, int rps,
                                                      float* __restrict__ out, int rows_per_block) {
+    pdl_sync();
     // block (32 x 32): x -> column, y -> row lane
     __shared__ float red[32][33];
     const int j = blockIdx.x * 32 + threadIdx.x;
@@ -194,17 +196,17 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 
 int launch_gemm(const GemmArgs& p, bool a_rc, bool b_rc, int splits, cudaStream_t st) {
     dim3 grid(ceil_div(p.I, BM), ceil_div(p.J, BN), splits);
-    if (a_rc && b_rc) gemm_kernel<true, true><<<grid, GT, 0, st>>>(p);
-    else if (a_rc && !b_rc) gemm_kernel<true, false><<<grid, GT, 0, st>>>(p);
-    else if (!a_rc && b_rc) gemm_kernel<false, true><<<grid, GT, 0, st>>>(p);
-    else gemm_kernel<false, false><<<grid, GT, 0, st>>>(p);
+    if (a_rc && b_rc) mic::launch((gemm_kernel<true, true>), grid, dim3(GT), 0, st, p);
+    else if (a_rc && !b_rc) mic::launch((gemm_kernel<true, false>), grid, dim3(GT), 0, st, p);
+    else if (!a_rc && b_rc) mic::launch((gemm_kernel<false, true>), grid, dim3(GT), 0, st, p);
+    else mic::launch((gemm_kernel<false, false>), grid, dim3(GT), 0, st, p);
     return check_launch("gemm_kernel");
 }
 
 int colsum(const float* X, int64_t ldx, int M, int N, const float* rowscale, int rps, float* out, cudaStream_t st) {
     int rows_per_block = M >= 16384 ? 512 : 128;
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
-    colsum_kernel<<<grid, dim3(32, 32), 0, st>>>(X, ldx, M, N, rowscale, rps, out, rows_per_block);
+    mic::launch(colsum_kernel, grid, dim3(32, 32), 0, st, X, ldx, M, N, rowscale, rps, out, rows_per_block);
     return check_launch("colsum_kernel");
 }
 

@@ -178,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();            // everything above touched only shared memory / TMEM: it overlaps the previous kernel
     if (threadIdx.x == 0) trace(1);
 
     if (warp == 0) {
@@ -476,6 +477,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();            // everything above touched only shared memory / TMEM: it overlaps the previous kernel
 
     // tile t -> (j fastest: CTAs that run concurrently share the A tile in L2)
     auto decode = [&](int t, int& i0, int& j0, int& kb0, int& nkb) {
@@ -816,7 +818,7 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
             cudaFuncSetAttribute(gemm_tcp_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
             attr_sz = 227 * 1024;                                                                                    \
         }                                                                                                            \
-        gemm_tcp_kernel<AM, BM_, EP><<<pgrid, TCP_THREADS, psmem, st>>>(mA, mB, mC, mP, e, sc, BNT, TCOLS);            \
+        mic::launch((gemm_tcp_kernel<AM, BM_, EP>), dim3(pgrid), dim3(TCP_THREADS), psmem, st, mA, mB, mC, mP, e, sc, BNT, TCOLS);            \
     } while (0)
 #define PLAUNCH_EPI(AM, BM_)                                                           \
     switch (epi) {                                                                     \
@@ -843,7 +845,7 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
                                  (int)(1024 + 12 * TM * TKB * 4 + 256 + 512));                                         \
             attr_done = true;                                                                                    \
         }                                                                                                        \
-        gemm_tc_kernel<AM, BM_, EP><<<grid, TC_THREADS, smem, st>>>(mA, mB, mC, mP, e, BNT, TCOLS);                       \
+        mic::launch((gemm_tc_kernel<AM, BM_, EP>), grid, dim3(TC_THREADS), smem, st, mA, mB, mC, mP, e, BNT, TCOLS);                       \
     } while (0)
 #define LAUNCH_EPI(AM, BM_)                                                            \
     switch (epi) {                                                                     \

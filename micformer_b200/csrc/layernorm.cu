@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, float* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, LnGeom g,
                                                      int64_t prows, float eps, int lpr) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int gl = lane % lpr, gi = lane / lpr, rpw = 32 / lpr;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ dres1, float* __restrict__ dx0,
                                                      float* __restrict__ dx1, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, LnGeom g, int64_t prows, int lpr) {
+    pdl_sync();
     extern __shared__ float red[];  // [2][C]
     const int lane = threadIdx.x & 31;
     const int gl = lane % lpr, gi = lane / lpr, rpw = 32 / lpr;
@@ -222,7 +224,7 @@ extern "C" int mic_layernorm_fwd(const float* x0, int C0, const float* x1, int C
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(V) ln_fwd_kernel<V><<<(unsigned)blocks, wpb * 32, 0, st>>>(x0, C0, x1, C1, gamma, beta, y, mean, rstd, g, prows, eps, lpr)
+#define LN_FWD(V) mic::launch((ln_fwd_kernel<V>), dim3((unsigned)blocks), dim3(wpb * 32), 0, st, x0, C0, x1, C1, gamma, beta, y, mean, rstd, g, prows, eps, lpr)
     switch (vpl) {
         case 1: LN_FWD(1); break;
         case 2: LN_FWD(2); break;
@@ -260,7 +262,7 @@ extern "C" int mic_layernorm_bwd(const float* dy, const float* x0, int C0, const
     const size_t smem = 2 * (size_t)C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define LN_BWD(V)                                                                                              \
-    ln_bwd_kernel<V><<<(unsigned)blocks, wpb * 32, smem, st>>>(dy, x0, C0, x1, C1, gamma, mean, rstd, dres0,   \
+    mic::launch((ln_bwd_kernel<V>), dim3((unsigned)blocks), dim3(wpb * 32), smem, st, dy, x0, C0, x1, C1, gamma, mean, rstd, dres0,   \
                                                                dres1, dx0, dx1, dgamma, dbeta, g, prows, lpr)
     switch (vpl) {
         case 1: LN_BWD(1); break;

@@ -10,6 +10,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) block_permute_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                             int Dq, int Hq, int Wq, int k, int C,
                                                             int64_t grid_batch_stride, int to_rows, int64_t total) {
+    pdl_sync();
     const int L = k * C;
     const int LV = L / VEC;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -39,6 +40,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restrict__ logits,
                                                            const float* __restrict__ target,
                                                            double* __restrict__ sums, int C, int64_t S) {
+    pdl_sync();
     // grid: (chunks, B*C); one (b,c) slab per blockIdx.y
     const int64_t slab = blockIdx.y;
     const int c = (int)(slab % C);
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restri
 
 __global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __restrict__ loss, float* __restrict__ coef,
                                      int C, double n) {
+    pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double dice = 0.0, ce = 0.0;
     for (int c = 0; c < C; ++c) {
@@ -104,6 +107,7 @@ __global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __r
 __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                        const float* __restrict__ coef, const float* __restrict__ dloss,
                                                        float* __restrict__ dlogits, int C, int64_t S) {
+    pdl_sync();
     const int64_t slab = blockIdx.y;
     const int c = (int)(slab % C);
     const float g = dloss ? *dloss : 1.f;
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(256) crop_residual_kernel(const float* __restr
                                                             const float* __restrict__ rowscale, float* __restrict__ y,
                                                             int D, int H, int W, int Dp, int Hp, int Wp, int C4,
                                                             int64_t total) {
+    pdl_sync();
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C4);
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256) crop_residual_bwd_kernel(const float* __r
                                                                 const float* __restrict__ rowscale,
                                                                 float* __restrict__ dbr, int D, int H, int W, int Dp,
                                                                 int Hp, int Wp, int C4, int64_t total) {
+    pdl_sync();
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C4);
@@ -183,10 +189,10 @@ extern "C" int mic_block_permute(const float* src, float* dst, int B, int Dq, in
                      ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     if (vec) {
         const int64_t total = (int64_t)B * Dq * Hq * Wq * k * k * (L / 4);
-        block_permute_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(src, dst, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, total);
+        mic::launch((block_permute_kernel<4>), dim3(grid_for(total, 256)), dim3(256), 0, st, src, dst, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, total);
     } else {
         const int64_t total = (int64_t)B * Dq * Hq * Wq * k * k * L;
-        block_permute_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(src, dst, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, total);
+        mic::launch((block_permute_kernel<1>), dim3(grid_for(total, 256)), dim3(256), 0, st, src, dst, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, total);
     }
     return check_launch("block_permute_kernel");
 }
@@ -198,14 +204,14 @@ extern "C" int mic_dice_bce_partial(const float* logits, const float* target, do
     const int cap = ceil_div(num_sms() * 8, B * C);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    dice_partial_kernel<<<dim3(chunks, B * C), 256, 0, (cudaStream_t)stream>>>(logits, target, sums, C, S);
+    mic::launch(dice_partial_kernel, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits, target, sums, C, S);
     return check_launch("dice_partial_kernel");
 }
 
 extern "C" int mic_dice_bce_finalize(const double* sums, float* loss, float* coef, int C, double n_per_channel,
                                      void* stream) {
     MIC_REQUIRE(sums && loss && coef && C > 0 && n_per_channel > 0, "dice_bce_finalize: bad arguments");
-    dice_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, loss, coef, C, n_per_channel);
+    mic::launch(dice_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, loss, coef, C, n_per_channel);
     return check_launch("dice_finalize_kernel");
 }
 
@@ -217,7 +223,7 @@ extern "C" int mic_dice_bce_bwd(const float* logits, const float* target, const 
     const int cap = ceil_div(num_sms() * 16, B * C);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    dice_bwd_kernel<<<dim3(chunks, B * C), 256, 0, (cudaStream_t)stream>>>(logits, target, coef, dloss, dlogits, C, S);
+    mic::launch(dice_bwd_kernel, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits, target, coef, dloss, dlogits, C, S);
     return check_launch("dice_bwd_kernel");
 }
 
@@ -225,7 +231,7 @@ extern "C" int mic_crop_residual(const float* res, const float* branch, const fl
                                  int H, int W, int Dp, int Hp, int Wp, int C, void* stream) {
     MIC_REQUIRE(res && branch && y && (C & 3) == 0, "crop_residual: bad arguments");
     const int64_t total = (int64_t)B * D * H * W * (C / 4);
-    crop_residual_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(res, branch, rowscale, y, D, H, W, Dp, Hp, Wp,
+    mic::launch(crop_residual_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, res, branch, rowscale, y, D, H, W, Dp, Hp, Wp,
                                                                                 C / 4, total);
     return check_launch("crop_residual_kernel");
 }
@@ -234,7 +240,7 @@ extern "C" int mic_crop_residual_bwd(const float* dy, const float* rowscale, flo
                                      int Dp, int Hp, int Wp, int C, void* stream) {
     MIC_REQUIRE(dy && dbranch && (C & 3) == 0, "crop_residual_bwd: bad arguments");
     const int64_t total = (int64_t)B * Dp * Hp * Wp * (C / 4);
-    crop_residual_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, rowscale, dbranch, D, H, W, Dp, Hp, Wp,
+    mic::launch(crop_residual_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, rowscale, dbranch, D, H, W, Dp, Hp, Wp,
                                                                                     C / 4, total);
     return check_launch("crop_residual_bwd_kernel");
 }

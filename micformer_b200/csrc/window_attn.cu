@@ -30,6 +30,7 @@ template <int HD>
 __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_fwd_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                        const float* __restrict__ v, int ldkv, float* __restrict__ out, int ldo,
                                        float* __restrict__ lse, WinGeom g, float scale) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     float* Ks = smem;                              // [G][N][HD]
     float* Vs = smem + (size_t)g.G * g.N * HD;     // [G][N][HD]
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_bwd_kernel(co
                                        const float* __restrict__ dout, int ldo, const float* __restrict__ lse,
                                        float* __restrict__ dq, int lddq, float* __restrict__ dk,
                                        float* __restrict__ dv, int lddkv, WinGeom g, float scale) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int N = g.N;
     const size_t GN = (size_t)g.G * N;
@@ -254,7 +256,7 @@ static int launch_fwd(const float* q, int ldq, const float* k, const float* v, i
     }
     const int threads = ceil_div(g.G * g.N, 32) * 32;
     const int64_t blocks = ceil_div64(g.ngroups, g.G);
-    kern<<<(unsigned)blocks, threads, smem, st>>>(q, ldq, k, v, ldkv, out, ldo, lse, g, scale);
+    mic::launch(kern, dim3((unsigned)blocks), dim3(threads), smem, st, q, ldq, k, v, ldkv, out, ldo, lse, g, scale);
     return check_launch("window_attn_fwd_kernel");
 }
 
@@ -274,7 +276,7 @@ static int launch_bwd(const float* q, int ldq, const float* k, const float* v, i
     }
     const int threads = ceil_div(g.G * g.N, 32) * 32;
     const int64_t blocks = ceil_div64(g.ngroups, g.G);
-    kern<<<(unsigned)blocks, threads, smem, st>>>(q, ldq, k, v, ldkv, out, dout, ldo, lse, dq, lddq, dk, dv, lddkv, g,
+    mic::launch(kern, dim3((unsigned)blocks), dim3(threads), smem, st, q, ldq, k, v, ldkv, out, dout, ldo, lse, dq, lddq, dk, dv, lddkv, g,
                                                   scale);
     return check_launch("window_attn_bwd_kernel");
 }

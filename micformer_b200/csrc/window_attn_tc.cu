@@ -174,6 +174,7 @@ window_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
+    pdl_sync();            // prologue above (ring clear, barriers, TMEM) overlaps the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -532,6 +533,7 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
+    pdl_sync();            // prologue above (ring clear, barriers, TMEM) overlaps the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -795,10 +797,10 @@ int tc_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, 
             cudaFuncSetAttribute(window_attn_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr2 = true;
         }
-        window_attn_tc2_fwd_kernel<<<(unsigned)grid, A2_THREADS, smem, st>>>(mQK, mV, a);
+        mic::launch(window_attn_tc2_fwd_kernel, dim3((unsigned)grid), dim3(A2_THREADS), smem, st, mQK, mV, a);
         return check_launch("window_attn_tc2_fwd_kernel");
     }
-    window_attn_tc_fwd_kernel<<<(unsigned)grid, AT_THREADS, smem, st>>>(mQK, mV, a);
+    mic::launch(window_attn_tc_fwd_kernel, dim3((unsigned)grid), dim3(AT_THREADS), smem, st, mQK, mV, a);
     return check_launch("window_attn_tc_fwd_kernel");
 }
 
