@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--no-attn-isolation", action="store_true")
+    ap.add_argument("--arena", type=int, default=int(os.environ.get("MICFORMER_GRAD_ARENA", "-1")),
+                    help="1: gradients accumulate directly into one flat buffer (micformer_b200.arena.GradArena) and the "
+                         "all-reduce runs in place on it; default: on for N > 1 (measured neutral at N = 1)")
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MICFORMER_GEMM_MODE", "1")),
                     help="1 (default): tcgen05 TF32 GEMMs/convs, logits within 1e-3 of the fp32 CPU path; 0: exact fp32")
     ap.add_argument("--profile-step", action="store_true",
@@ -183,7 +186,12 @@ def run_ours(args):
     crit = MDiceLoss()
     from micformer_b200.optim import FusedAdam
     opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)          # train_mmwhs_noPad.py:114
-    sync = GradSync(list(model.parameters()))
+    arena = None
+    if args.arena == 1 or (args.arena < 0 and world > 1):
+        from micformer_b200.arena import GradArena
+        arena = GradArena(model.parameters())      # .grad slices of one flat buffer: 1 memset, in-place all-reduce
+        opt.attach_arena(arena)
+    sync = GradSync(list(model.parameters()), arena=arena)
     x_h, lab_h = O.synth_inputs(B, S, cfg.num_classes, seed=1 + rank)
     x_h, lab_h = x_h.pin_memory(), lab_h.pin_memory()
     x_d, lab_d = x_h.to(dev), lab_h.to(dev)
@@ -231,6 +239,8 @@ def run_ours(args):
         graph = torch.cuda.CUDAGraph()
         _native.reset_launch_count()
         with torch.cuda.graph(graph):
+            if arena is not None:
+                arena.zero()                       # one memset node; without the arena the grads are re-created per replay
             loss_static = crit(model(x_d), lab_d)
             loss_static.backward()
             sync.sync()

@@ -15,15 +15,18 @@ struct WinGeom {
     int64_t ngroups;     // B * nW * heads
 };
 
-__device__ __forceinline__ int64_t token_row(const WinGeom& g, int64_t win, int tok) {
-    // win = ((b*nwd + wz)*nwh + wy)*nww + wx ; tok = (iz*wh + iy)*ww + ix
-    const int wx = (int)(win % g.nww); win /= g.nww;
-    const int wy = (int)(win % g.nwh); win /= g.nwh;
-    const int wz = (int)(win % g.nwd); win /= g.nwd;
-    const int ix = tok % g.ww; tok /= g.ww;
-    const int iy = tok % g.wh; tok /= g.wh;
-    const int z = wz * g.wd + tok, y = wy * g.wh + iy, x = wx * g.ww + ix;
-    return ((win * g.Dp + z) * g.Hp + y) * (int64_t)g.Wp + x;
+__device__ __forceinline__ int64_t token_row(const WinGeom& g, int64_t win64, int tok) {
+    // win = ((b*nwd + wz)*nwh + wy)*nww + wx ; tok = (iz*wh + iy)*ww + ix.  32-bit index math (the host checks that
+    // the window count fits): 64-bit div/mod is a ~100-instruction software routine and this runs per staged float4
+    uint32_t win = (uint32_t)win64;
+    const uint32_t wx = win % (uint32_t)g.nww; win /= (uint32_t)g.nww;
+    const uint32_t wy = win % (uint32_t)g.nwh; win /= (uint32_t)g.nwh;
+    const uint32_t wz = win % (uint32_t)g.nwd; win /= (uint32_t)g.nwd;
+    uint32_t t = (uint32_t)tok;
+    const uint32_t ix = t % (uint32_t)g.ww; t /= (uint32_t)g.ww;
+    const uint32_t iy = t % (uint32_t)g.wh; t /= (uint32_t)g.wh;
+    const uint32_t z = wz * g.wd + t, y = wy * g.wh + iy, x = wx * g.ww + ix;
+    return (((int64_t)win * g.Dp + z) * g.Hp + y) * (int64_t)g.Wp + x;
 }
 
 template <int HD>
@@ -44,8 +47,8 @@ __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_fwd_kernel(co
         const int gg = idx / (V4 * N);
         const int64_t grp = group0 + gg;
         if (grp >= g.ngroups) continue;
-        const int head = (int)(grp % g.heads);
-        const int64_t row = token_row(g, grp / g.heads, tok);
+        const int head = (int)((uint32_t)grp % (uint32_t)g.heads);
+        const int64_t row = token_row(g, (uint32_t)grp / (uint32_t)g.heads, tok);
         const float4 kk = *reinterpret_cast<const float4*>(k + row * ldkv + head * HD + part * 4);
         const float4 vv = *reinterpret_cast<const float4*>(v + row * ldkv + head * HD + part * 4);
         *reinterpret_cast<float4*>(Ks + ((size_t)gg * N + tok) * HD + part * 4) = kk;
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_fwd_kernel(co
     const int gg = threadIdx.x / N, i = threadIdx.x % N;
     const int64_t grp = group0 + gg;
     if (gg >= g.G || grp >= g.ngroups) return;
-    const int head = (int)(grp % g.heads);
-    const int64_t row = token_row(g, grp / g.heads, i);
+    const int head = (int)((uint32_t)grp % (uint32_t)g.heads);
+    const int64_t row = token_row(g, (uint32_t)grp / (uint32_t)g.heads, i);
     float qr[HD], acc[HD];
 #pragma unroll
     for (int c = 0; c < V4; ++c) {
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_bwd_kernel(co
         const int gg = idx / (V4 * N);
         const int64_t grp = group0 + gg;
         if (grp >= g.ngroups) continue;
-        const int head = (int)(grp % g.heads);
-        const int64_t row = token_row(g, grp / g.heads, tok);
+        const int head = (int)((uint32_t)grp % (uint32_t)g.heads);
+        const int64_t row = token_row(g, (uint32_t)grp / (uint32_t)g.heads, tok);
         const size_t so = ((size_t)gg * N + tok) * HD + part * 4;
         *reinterpret_cast<float4*>(Qs + so) = *reinterpret_cast<const float4*>(q + row * ldq + head * HD + part * 4);
         *reinterpret_cast<float4*>(Ks + so) = *reinterpret_cast<const float4*>(k + row * ldkv + head * HD + part * 4);
@@ -139,8 +142,8 @@ __global__ void __launch_bounds__(HD > 32 ? 128 : 384) window_attn_bwd_kernel(co
     int head = 0;
     int64_t row = 0;
     if (active) {
-        head = (int)(grp % g.heads);
-        row = token_row(g, grp / g.heads, i);
+        head = (int)((uint32_t)grp % (uint32_t)g.heads);
+        row = token_row(g, (uint32_t)grp / (uint32_t)g.heads, i);
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < V4; ++c) {
@@ -238,6 +241,7 @@ static int make_geom(WinGeom& g, int B, int Dp, int Hp, int Wp, int heads, int w
     if (g.N > 384) return fail(MIC_ERR_UNSUPPORTED, "window_attn: %d tokens per window > 384", g.N);
     g.G = g.N >= 128 ? 1 : 128 / g.N;
     g.ngroups = (int64_t)B * g.nwd * g.nwh * g.nww * heads;
+    if (g.ngroups >= (int64_t)1 << 31) return fail(MIC_ERR_UNSUPPORTED, "window_attn: more than 2^31 (window, head) groups");
     return MIC_OK;
 }
 

@@ -66,6 +66,26 @@ def _zeros(shape, like: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# gradient arena: when ``micformer_b200.arena.GradArena`` is attached, every parameter's ``.grad`` is a slice of one
+# flat buffer that is cleared with ONE memset per step.  The weight-gradient kernels all accumulate (TMA reduce-add /
+# atomics), so backward writes straight into ``p.grad`` and returns None for that input: no per-block zero fills, no
+# AccumulateGrad copies / adds for shared modules, and the data-parallel all-reduce runs in place on the flat buffer.
+# ----------------------------------------------------------------------------------------------------------
+def _acc(p) -> Optional[Tensor]:
+    """``p.grad`` when it is arena-backed (accumulate into it directly), else None"""
+    if p is not None and getattr(p, "_mic_arena", False):
+        g = p.grad
+        if g is not None and g.is_contiguous() and g.dtype == torch.float32:
+            return g
+    return None
+
+
+def _gret(p, t):
+    """what backward returns for parameter ``p`` whose gradient was produced in ``t``"""
+    return None if _acc(p) is not None else t
+
+
+# ----------------------------------------------------------------------------------------------------------
 # weight-gradient side branch: dW / db kernels do not feed the data-gradient chain, so each backward forks them
 # onto an auxiliary stream (one per calling stream) and joins before returning.  Under CUDA-graph capture this
 # becomes a parallel branch; buffers are allocated on the calling stream before the fork and the join precedes
@@ -131,18 +151,19 @@ def ln_fwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, beta: Tensor, dims, 
 
 
 def ln_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
-           dres0: Optional[Tensor], dres1: Optional[Tensor], dims, pdims=None):
+           dres0: Optional[Tensor], dres1: Optional[Tensor], dims, pdims=None, beta=None):
+    """``beta``: the bias Parameter (only needed to find its arena gradient; dgamma goes to ``gamma``'s)."""
     B, D, H, W = dims
     Dp, Hp, Wp = pdims if pdims is not None else (D, H, W)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     dx0 = torch.empty_like(x0)
     dx1 = torch.empty_like(x1) if x1 is not None else None
-    dgamma = _zeros((C0 + C1,), x0)
-    dbeta = _zeros((C0 + C1,), x0)
+    dgamma = _acc(gamma) if _acc(gamma) is not None else _zeros((C0 + C1,), x0)
+    dbeta = _acc(beta) if _acc(beta) is not None else _zeros((C0 + C1,), x0)
     N.call("mic_layernorm_bwd", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(gamma), N.ptr(mean), N.ptr(rstd),
            N.ptr(dres0), N.ptr(dres1), N.ptr(dx0), N.ptr(dx1), N.ptr(dgamma), N.ptr(dbeta), B, D, H, W, Dp, Hp, Wp)
-    return dx0, dx1, dgamma, dbeta
+    return dx0, dx1, _gret(gamma, dgamma), _gret(beta, dbeta)
 
 
 def _view_ptr(t: Tensor, col: int) -> int:
@@ -192,16 +213,27 @@ def linear_bwd_weight(dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: 
     return dW, db
 
 
-def linear_bwd_weight_side(sb: "side_branch", dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: int, K: int, **kw):
-    """linear_bwd_weight on the side branch; outputs are allocated (zeroed) on the calling stream first."""
+def linear_bwd_weight_side(sb: "side_branch", dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: int, K: int,
+                           wp=None, bp=None, **kw):
+    """linear_bwd_weight on the side branch; outputs are allocated (zeroed) on the calling stream first.
+    ``wp`` / ``bp``: the weight / bias Parameters -- with a gradient arena attached the kernels accumulate straight into
+    their ``.grad`` (row-major (Nout, K) weight, or a row slice of it selected by ``dw_row0``) and None is returned."""
     w_is_kn = kw.get("w_is_kn", False)
+    row0 = kw.pop("dw_row0", 0)
+    gw, gb = _acc(wp), _acc(bp)
+    if gw is not None and kw.get("dW") is None and not w_is_kn:
+        kw["dW"] = gw.view(-1, K)[row0:row0 + Nout]
+        kw["lddw"] = K
+    if gb is not None and kw.get("db") is None and kw.get("want_bias", True):
+        kw["db"] = gb[row0:row0 + Nout]
     if kw.get("dW") is None:
         kw["dW"] = _zeros((K, Nout) if w_is_kn else (Nout, K), dY)
         kw["lddw"] = Nout if w_is_kn else K
     if kw.get("db") is None and kw.get("want_bias", True):
         kw["db"] = _zeros((Nout,), dY)
     sb.hold(dY, X, kw.get("rowscale"))
-    return sb.run(linear_bwd_weight, dY, lddy, X, ldx, M, Nout, K, **kw)
+    dW, db = sb.run(linear_bwd_weight, dY, lddy, X, ldx, M, Nout, K, **kw)
+    return (None if gw is not None and not w_is_kn else dW), (None if gb is not None else db)
 
 
 def window_attn_fwd(qkv: Tensor, C: int, heads: int, B: int, pdims, ws):
@@ -306,18 +338,18 @@ def _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded):
     return crop_add(x, pr, s1, dims, pdims)
 
 
-def _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded):
+def _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb=None):
     """-> do_p (P,C), dpw, dpb"""
     B, D, H, W = dims
     C = dx1.shape[-1]
     if not padded:
         T = B * D * H * W
-        dpw, dpb = linear_bwd_weight_side(sb, dx1, C, o_p, C, T, C, C, rowscale=s1, rps=D * H * W)
+        dpw, dpb = linear_bwd_weight_side(sb, dx1, C, o_p, C, T, C, C, wp=pw, bp=pb, rowscale=s1, rps=D * H * W)
         do_p = linear_bwd_data(dx1, C, pw, T, C, C, rowscale=s1, rps=D * H * W)
         return do_p, dpw, dpb
     P = B * pdims[0] * pdims[1] * pdims[2]
     dpr = crop_bwd(dx1, s1, dims, pdims)
-    dpw, dpb = linear_bwd_weight_side(sb, dpr, C, o_p, C, P, C, C)
+    dpw, dpb = linear_bwd_weight_side(sb, dpr, C, o_p, C, P, C, C, wp=pw, bp=pb)
     do_p = linear_bwd_data(dpr, C, pw, P, C, C)
     return do_p, dpw, dpb
 
@@ -334,7 +366,7 @@ def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims):
     return y, (xn2, mean2, rstd2, hpre, h)
 
 
-def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims):
+def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims, n2b=None, f1b=None, f2b=None):
     """-> dx1 (= dy + grad through LN/MLP), dn2w, dn2b, df1w, df1b, df2w, df2b"""
     xn2, mean2, rstd2, hpre, h = saved
     B, D, H, W = dims
@@ -342,11 +374,11 @@ def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims):
     T = B * D * H * W
     Hd = f1w.shape[0]
     rps = D * H * W
-    df2w, df2b = linear_bwd_weight_side(sb, dy, C, h, Hd, T, C, Hd, rowscale=s2, rps=rps)
+    df2w, df2b = linear_bwd_weight_side(sb, dy, C, h, Hd, T, C, Hd, wp=f2w, bp=f2b, rowscale=s2, rps=rps)
     dh = linear_bwd_data(dy, C, f2w, T, C, Hd, gelu_pre=hpre, rowscale=s2, rps=rps)
-    df1w, df1b = linear_bwd_weight_side(sb, dh, Hd, xn2, C, T, Hd, C)
+    df1w, df1b = linear_bwd_weight_side(sb, dh, Hd, xn2, C, T, Hd, C, wp=f1w, bp=f1b)
     dxn2 = linear_bwd_data(dh, Hd, f1w, T, Hd, C)
-    dx1, _, dn2w, dn2b = ln_bwd(dxn2, x1, None, n2w, mean2, rstd2, dy, None, dims)
+    dx1, _, dn2w, dn2b = ln_bwd(dxn2, x1, None, n2w, mean2, rstd2, dy, None, dims, beta=n2b)
     return dx1, dn2w, dn2b, df1w, df1b, df2w, df2b
 
 
@@ -374,12 +406,14 @@ class SelfBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, xn_p, mean1, rstd1, qkv, o_p, lse, x1, *mlp_saved, n1w, qw, kvw, pw, n2w, f1w, f2w,
                               *( [s1] if s1 is not None else []), *([s2] if s2 is not None else []))
         ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
+        ctx.biases = (n1b, qb, kvb, pb, n2b, f1b, f2b)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         dims, pdims, ws, padded, heads, has1, has2 = ctx.meta
+        n1b, qb, kvb, pb, n2b, f1b, f2b = ctx.biases
         sv = list(ctx.saved_tensors)
         x, xn_p, mean1, rstd1, qkv, o_p, lse, x1 = sv[:8]
         mlp_saved = sv[8:13]
@@ -392,14 +426,14 @@ class SelfBlockFn(torch.autograd.Function):
         P = B * pdims[0] * pdims[1] * pdims[2]
         dy = dy.contiguous()
         with zero_arena(12 * C * C + 128 * C + 4096, x), side_branch() as sb:
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded)
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b)
+            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
-            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C)
-            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, 2 * C, C, dy_col=C)
+            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
+            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, 2 * C, C, wp=kvw, bp=kvb, dy_col=C)
             dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
             linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
-            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
                 df2b)
 
@@ -443,12 +477,14 @@ class CrossBlockFn(torch.autograd.Function):
                               pw, cw, lnw, lnb, w3, n2w, f1w, f2w, *([s1] if s1 is not None else []),
                               *([s2] if s2 is not None else []))
         ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
+        ctx.biases = (n1b, qb, kvb, pb, cb, n2b, f1b, f2b)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         dims, pdims, ws, padded, heads, has1, has2 = ctx.meta
+        n1b, qb, kvb, pb, cb, n2b, f1b, f2b = ctx.biases
         sv = list(ctx.saved_tensors)
         x, xa_p, xn_p, mean1, rstd1, h16, pos, samp, qkv, o_p, lse, x1 = sv[:12]
         mlp_saved = sv[12:17]
@@ -463,11 +499,11 @@ class CrossBlockFn(torch.autograd.Function):
         HC = cw.shape[-1]
         dy = dy.contiguous()
         with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x), side_branch() as sb:
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims)
-            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded)
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b)
+            do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
-            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C)
-            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, samp, C, P, 2 * C, C, dy_col=C)
+            dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
+            dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, samp, C, P, 2 * C, C, wp=kvw, bp=kvb, dy_col=C)
             dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
             dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
             dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
@@ -475,19 +511,23 @@ class CrossBlockFn(torch.autograd.Function):
             N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa_p), N.ptr(pos), N.ptr(dxa_p), N.ptr(dpos), B, Dp, Hp, Wp, Dp,
                    Hp, Wp, C)
             dh16 = _empty((P, HC), x)
-            dlnw = _zeros((HC,), x); dlnb = _zeros((HC,), x); dw3 = _zeros((3, HC), x)
+            dlnw = _acc(lnw) if _acc(lnw) is not None else _zeros((HC,), x)
+            dlnb = _acc(lnb) if _acc(lnb) is not None else _zeros((HC,), x)
+            dw3 = _zeros((3, HC), x)
             N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
                    N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
-            dcw = _zeros(tuple(cw.shape), x); dcb = _zeros((HC,), x)
+            dlnw, dlnb = _gret(lnw, dlnw), _gret(lnb, dlnb)
+            dcw = _zeros(tuple(cw.shape), x)
+            dcb = _acc(cb) if _acc(cb) is not None else _zeros((HC,), x)
             sb.hold(dh16, xn_p, xa_p)
             sb.run(conv3_bwd_weight, dh16, xn_p, xa_p, dcw, dcb, B, (Dp, Hp, Wp), HC, False)
             conv3_bwd_data(dh16, cw, dxn_p.view(B, Dp, Hp, Wp, C), True, dxa_p, True, B, (Dp, Hp, Wp), HC, False)
-            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims)
+            dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         if padded:
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
         else:
             dxa = dxa_p
-        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, None, dcb, dlnw, dlnb, dw3,
+        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, None, _gret(cb, dcb), dlnw, dlnb, dw3,
                 dn2w, dn2b, df1w, df1b, df2w, df2b)
 
 
@@ -507,6 +547,7 @@ class LayerNormFn(torch.autograd.Function):
         y, mean, rstd = ln_fwd(x0, x1, w, b, dims)
         ctx.save_for_backward(x0, x1 if x1 is not None else x0, w, mean, rstd)
         ctx.meta = (dims, x1 is not None)
+        ctx.beta = b
         C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
         return y.view(*x0.shape[:-1], C)
 
@@ -515,7 +556,7 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x0, x1, w, mean, rstd = ctx.saved_tensors
         dims, has1 = ctx.meta
-        dx0, dx1, dw, db = ln_bwd(dy.contiguous(), x0, x1 if has1 else None, w, mean, rstd, None, None, dims)
+        dx0, dx1, dw, db = ln_bwd(dy.contiguous(), x0, x1 if has1 else None, w, mean, rstd, None, None, dims, beta=ctx.beta)
         return dx0, dx1, dw, db
 
 
@@ -531,6 +572,7 @@ class SkipLinearFn(torch.autograd.Function):
         y = linear_fwd(a, Ca, w, bias, T, Cout, Ca, ldw=Ca + Cb)
         linear_fwd(b, Cb, w, None, T, Cout, Cb, ldw=Ca + Cb, w_col=Ca, out=y, ldy=Cout, accumulate=True)
         ctx.save_for_backward(a, b, w)
+        ctx.bias = bias
         return y.view(*a.shape[:-1], Cout)
 
     @staticmethod
@@ -543,10 +585,10 @@ class SkipLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         da = linear_bwd_data(dy, Cout, w, T, Cout, Ca, ldw=Ca + Cb).view(a.shape)
         db_ = linear_bwd_data(dy, Cout, w, T, Cout, Cb, ldw=Ca + Cb, w_col=Ca).view(b.shape)
-        dW = torch.zeros_like(w)
-        _, dbias = linear_bwd_weight(dy, Cout, a, Ca, T, Cout, Ca, dW=dW, lddw=Ca + Cb)
+        dW = _acc(w) if _acc(w) is not None else torch.zeros_like(w)
+        _, dbias = linear_bwd_weight(dy, Cout, a, Ca, T, Cout, Ca, dW=dW, lddw=Ca + Cb, db=_acc(ctx.bias))
         linear_bwd_weight(dy, Cout, b, Cb, T, Cout, Cb, dW=dW, lddw=Ca + Cb, dw_col=Ca, want_bias=False)
-        return da, db_, dW, dbias
+        return da, db_, _gret(w, dW), _gret(ctx.bias, dbias)
 
 
 def block_permute(src: Tensor, dst: Tensor, B, Dq, Hq, Wq, k, C, grid_batch_stride, to_rows, src_off=0):
@@ -603,6 +645,7 @@ class PatchMergeFn(torch.autograd.Function):
         y, mean, rstd = ln_fwd(z, None, nw, nb, (B, Dq, Hq, Wq))
         ctx.save_for_backward(rows, z, mean, rstd, w2, nw)
         ctx.meta = (B, Dq, Hq, Wq, C, Co)
+        ctx.nb = nb
         return y
 
     @staticmethod
@@ -611,7 +654,7 @@ class PatchMergeFn(torch.autograd.Function):
         rows, z, mean, rstd, w2, nw = ctx.saved_tensors
         B, Dq, Hq, Wq, C, Co = ctx.meta
         R = B * Dq * Hq * Wq
-        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, Dq, Hq, Wq))
+        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, Dq, Hq, Wq), beta=ctx.nb)
         drows = linear_bwd_data(dz, Co, w2, R, Co, 8 * C)
         dW, db = linear_bwd_weight(dz, Co, rows, 8 * C, R, Co, 8 * C)
         dx = _empty((B, 2 * Dq, 2 * Hq, 2 * Wq, C), dz)
@@ -635,6 +678,7 @@ class PatchExpandFn(torch.autograd.Function):
         y, mean, rstd = ln_fwd(z, None, nw, nb, (B, 2 * D, 2 * H, 2 * W))
         ctx.save_for_backward(x, z, mean, rstd, wk, nw)
         ctx.meta = (B, D, H, W, C, Co)
+        ctx.nb = nb
         return y
 
     @staticmethod
@@ -643,7 +687,7 @@ class PatchExpandFn(torch.autograd.Function):
         x, z, mean, rstd, wk, nw = ctx.saved_tensors
         B, D, H, W, C, Co = ctx.meta
         T = B * D * H * W
-        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, 2 * D, 2 * H, 2 * W))
+        dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, 2 * D, 2 * H, 2 * W), beta=ctx.nb)
         drows = _empty((T, 8 * Co), dz)
         block_permute(dz, drows, B, D, H, W, 2, Co, 8 * D * H * W * Co, True)
         dx = linear_bwd_data(drows, 8 * Co, wk, T, 8 * Co, C, w_is_kn=True).view(x.shape)
@@ -680,6 +724,7 @@ class SegHeadFn(torch.autograd.Function):
         N.set_gemm_mode(_mode)
         ctx.save_for_backward(xm, xf, n2w, mean, rstd, xn, wr, y24, wo)
         ctx.meta = (B, D, H, W, E, Ch, NC)
+        ctx.pb = (n2b, bo)
         return logits
 
     @staticmethod
@@ -691,15 +736,17 @@ class SegHeadFn(torch.autograd.Function):
         dlog = dlog.contiguous()
         dy24 = torch.empty_like(y24)
         conv3_bwd_data(dlog, wo, dy24, False, None, False, B, (4 * D, 4 * H, 4 * W), NC, True)
-        dwo = torch.zeros_like(wo); dbo = _zeros((NC,), xm)
+        n2b, bo = ctx.pb
+        dwo = torch.zeros_like(wo)
+        dbo = _acc(bo) if _acc(bo) is not None else _zeros((NC,), xm)
         conv3_bwd_weight(dlog, y24, None, dwo, dbo, B, (4 * D, 4 * H, 4 * W), NC, True)
         drows = _empty((T, 64 * Ch), xm)
         block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
         del dy24
         dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
         dwr, dbr64 = linear_bwd_weight(drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
-        dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W))
-        return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, None, dbo
+        dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W), beta=n2b)
+        return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, None, _gret(bo, dbo)
 
 
 class DiceBceLossFn(torch.autograd.Function):

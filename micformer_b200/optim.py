@@ -22,6 +22,18 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables = None
         self._grad_ptrs_host = None
         self._lr_on_device = None
+        self.arena = None
+
+    def attach_arena(self, arena) -> None:
+        """``micformer_b200.arena.GradArena``: ``zero_grad()`` then clears the flat buffer with one memset and keeps the
+        parameters pointing into it (whatever ``set_to_none`` says)."""
+        self.arena = arena
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        if self.arena is not None:
+            self.arena.zero()
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     # ---- state in torch.optim.Adam's layout --------------------------------------------------------------
     def _init_state(self):

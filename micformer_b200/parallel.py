@@ -16,12 +16,13 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None):
+    def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None, arena=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.group = process_group
         self._plan = None      # list of lists of param indices
         self._flat = None
+        self.arena = arena     # GradArena: the gradients already live in one flat buffer -> one in-place all-reduce
 
     @property
     def world(self) -> int:
@@ -52,6 +53,11 @@ class GradSync:
     def sync(self) -> None:
         """Average ``.grad`` across ranks in place.  Call after ``backward()``."""
         if self.world <= 1:
+            return
+        if self.arena is not None and self.arena.attached():
+            # parameters without a gradient (concat_back_dim.0) hold zeros on every rank: harmless to include
+            self.arena.flat.mul_(1.0 / self.world)
+            dist.all_reduce(self.arena.flat, group=self.group)
             return
         if self._plan is None:
             self._build_plan()

@@ -61,3 +61,47 @@ def test_fused_adam_inside_cuda_graph():
     torch.cuda.synchronize()
     for pa, pb in zip(a, b):
         assert float((pa - pb).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_grad_arena_direct_accumulation_matches_autograd(mode):
+    """With a GradArena attached, backward writes straight into the flat gradient buffer: same gradients as the
+    ordinary autograd path, accumulation across two backward passes, one memset to clear."""
+    from micformer_b200 import _native as N
+    from micformer_b200.arena import GradArena
+    from micformer_b200.models.MICFormer_self import Head, MicFormer
+    from micformer_b200.loss.dice import MDiceLoss
+    from oracle import micformer_oracle as O
+    prev = N.get_gemm_mode()
+    N.set_gemm_mode(mode)
+    try:
+        cfg = O.TINY
+        sd = O.synth_state_dict(cfg, seed=3)
+        head = Head(embed_dim=cfg.embed_dim, num_classes=cfg.num_classes, window_size=cfg.window_size)
+        head.swin = MicFormer(window_size=cfg.window_size, in_chans=1, embed_dim=cfg.embed_dim, depths=list(cfg.depths),
+                              num_heads=list(cfg.num_heads))
+        head.load_state_dict(sd, strict=True)
+        head = head.cuda().eval()
+        x, lab = O.synth_inputs(1, 64, cfg.num_classes, seed=5)
+        x, lab = x.cuda(), lab.cuda()
+        MDiceLoss()(head(x), lab).backward()
+        ref = {k: (p.grad.clone() if p.grad is not None else None) for k, p in head.named_parameters()}
+        for p in head.parameters():
+            p.grad = None
+        arena = GradArena(head.parameters())
+        MDiceLoss()(head(x), lab).backward()
+        assert arena.attached()
+        gl2 = float(sum((g.double() ** 2).sum() for g in ref.values() if g is not None) ** 0.5)
+        tol = 1e-4 if mode == 0 else 2e-2          # TF32 split-R partial sums are reduced in a different order
+        for k, p in head.named_parameters():
+            if ref[k] is None:
+                assert float(p.grad.abs().max()) == 0.0, k
+            else:
+                assert float((p.grad - ref[k]).norm() / (ref[k].norm() + 1e-5 * gl2)) < tol, k
+        once = arena.flat.clone()
+        MDiceLoss()(head(x), lab).backward()       # gradients accumulate, as with zero_grad(set_to_none=False)
+        assert float((arena.flat - 2 * once).norm() / once.norm()) < (1e-4 if mode == 0 else 2e-2)
+        arena.zero()
+        assert float(arena.flat.abs().max()) == 0.0 and arena.attached()
+    finally:
+        N.set_gemm_mode(prev)

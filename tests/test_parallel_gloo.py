@@ -32,6 +32,14 @@ def _worker(rank, world, port, out):
     plist = list(params.values())
     gs = GradSync(plist, bucket_bytes=1 << 20)
     gs.sync()
+    # the same exchange through a gradient arena: one in-place all-reduce of the flat buffer
+    from micformer_b200.arena import GradArena
+    params2 = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items()}
+    arena = GradArena(params2.values())
+    (O.head_forward(x[rank:rank + 1], params2, cfg) * lab[rank:rank + 1]).mean().backward()
+    assert arena.attached()
+    GradSync(list(params2.values()), arena=arena).sync()
+    arena_diff = max(float((params2[k].grad - params[k].grad).abs().max()) for k in params if params[k].grad is not None)
     if rank == 0:
         ref = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items()}
         full = O.head_forward(x, ref, cfg)
@@ -44,7 +52,7 @@ def _worker(rank, world, port, out):
                 continue
             worst = max(worst, float((params[k].grad - ref[k].grad).norm() / (ref[k].grad.norm() + 1e-5 * gl2)))
         skipped = [list(params.keys())[i] for i in gs.skipped()]
-        torch.save({"worst": worst, "skipped": skipped, "buckets": len(gs._plan)}, out)
+        torch.save({"worst": worst, "skipped": skipped, "buckets": len(gs._plan), "arena_diff": arena_diff}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,3 +66,4 @@ def test_gradsync_world2_matches_single_process(tmp_path):
     assert res["worst"] < 1e-4, res
     assert sorted(res["skipped"]) == ["swin.concat_back_dim.0.bias", "swin.concat_back_dim.0.weight"]
     assert res["buckets"] > 1
+    assert res["arena_diff"] < 1e-6, res
