@@ -272,17 +272,37 @@ def run_ours(args):
     clk = clocks.stop()
     value = world * B * args.steps / (ms / 1e3)
 
-    # --- end to end through the public API: pinned host -> device copies + loss read-back each step ------
+    # --- end to end through the public API: every step copies its inputs from pinned host memory and reads the loss
+    #     back.  The copies are issued the way a prefetching loader does it (pin_memory + non_blocking on a copy
+    #     stream, one step ahead, into staging buffers); the step itself starts with a device-to-device move into the
+    #     graph's static inputs.  One full H2D transfer of x and the labels is inside every timed step.
+    copy_stream = torch.cuda.Stream()
+    x_stage, lab_stage = torch.empty_like(x_d), torch.empty_like(lab_d)
+    copied, stage_free = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch():
+        copy_stream.wait_event(stage_free)
+        with torch.cuda.stream(copy_stream):
+            x_stage.copy_(x_h, non_blocking=True)
+            lab_stage.copy_(lab_h, non_blocking=True)
+            copied.record(copy_stream)
+
     def e2e_step():
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied)                     # this step's inputs have landed in the staging buffers
         if graph is not None:
-            x_d.copy_(x_h, non_blocking=True)      # pinned host -> the graph's static input buffers
-            lab_d.copy_(lab_h, non_blocking=True)
+            x_d.copy_(x_stage); lab_d.copy_(lab_stage)
+            stage_free.record(cur)
+            prefetch()                             # next step's H2D overlaps this step's compute
             graph.replay()
             return float(loss_static.detach())     # D2H read of the loss (train_mmwhs_noPad.py:189-197)
-        x = x_h.to(dev, non_blocking=True)
-        lab = lab_h.to(dev, non_blocking=True)
+        x, lab = x_stage.clone(), lab_stage.clone()
+        stage_free.record(cur)
+        prefetch()
         return float(step(x, lab).detach())
 
+    stage_free.record(torch.cuda.current_stream())
+    prefetch()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)

@@ -32,6 +32,17 @@ constexpr int AHEAD = RING - 3;                // plane-chunks in flight ahead o
 constexpr int PL = (PPOS * KJ + 127) / 128;    // 16-byte elements per producer thread per plane-chunk (3)
 constexpr int CT_THREADS = 160;
 
+// optional phase trace of CTA 0 (debug): u64 globaltimer stamps, [event][index]
+__device__ unsigned long long* g_conv_trace = nullptr;
+__device__ __forceinline__ void ctrace(int ev, int idx) {
+    unsigned long long* t = g_conv_trace;
+    if (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && idx < 256) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        t[ev * 256 + idx] = now;
+    }
+}
+
 struct ConvTcGeom {
     int B, D, H, W;
     int C0, C1;            // input channels: x0 | x1 (channels-last), or C0 planes of an NCDHW tensor (in_ncdhw)
@@ -170,6 +181,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
             const int z = zs - 1 + pz;
             const int slot = n % RING;
             cbar_wait(&pempty[slot], ((n / RING) & 1) ^ 1);
+            if (tid == 0) ctrace(0, n);                          // slot free, copies of plane-chunk n issued
             const bool zok = z >= 0 && z < g.D;
             const uint32_t sbase = ring_u32 + slot * PLANE_BYTES;
 #pragma unroll
@@ -219,6 +231,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
             // groups committed so far: ahead + n; plane-chunk n is group n
             if (ahead == AHEAD) asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
             else asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 2) : "memory");
+            if (tid == 0) ctrace(1, n);                          // plane-chunk n landed (this thread's part)
             const int ch = n / ppc, pz = n - ch * ppc;
             const int slot = n % RING;
             uint8_t* sbase = ring + slot * PLANE_BYTES;
@@ -239,12 +252,15 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             cbar_arrive(&pfull[slot]);
+            if (tid == 0) ctrace(2, n);                          // published
             if (n + ahead < total) issue(n + ahead);
             else asm volatile("cp.async.commit_group;" ::: "memory");          // keep the group count uniform
         }
         // ------------------------------------------------------------------ epilogue
+        if (tid == 0) ctrace(5, 0);
         cbar_wait(accdone, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) ctrace(5, 1);
         const int q = warp;                                   // TMEM lane quarter
         const int r = q * 32 + lane;                          // row in the 128-position plane tile
         const int yy = yb + r / TX, xx = xb + r % TX;
@@ -319,6 +335,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
                     cbar_wait(&pfull[waited % RING], (waited / RING) & 1);
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                ctrace(3, ch * nz + zi);                          // MMA: planes of output plane (ch, zi) ready
                 const uint32_t dcol = tmem + (uint32_t)(zi * NT);
                 for (int tz = 0; tz < 3; ++tz) {
                     const uint32_t pbase = ring_addr + (uint32_t)(((n0p + zi + tz) % RING) * PLANE_BYTES);
@@ -333,6 +350,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
                         }
                 }
                 ccommit(&pempty[(n0p + zi) % RING]);              // plane z-1 is no longer needed
+                ctrace(4, ch * nz + zi);                          // MMAs issued
             }
             ccommit(&pempty[(n0p + nz) % RING]);                  // the last two planes of this chunk
             ccommit(&pempty[(n0p + nz + 1) % RING]);
@@ -340,6 +358,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
         }
         ccommit(accdone);
     }
+    if (threadIdx.x == 0) ctrace(5, 2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) {
@@ -419,6 +438,11 @@ int tc_conv3_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int 
 }
 
 }  // namespace mic
+extern "C" int mic_debug_conv_trace(void* buf) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(mic::g_conv_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+
 extern "C" int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1, const float* Wk, const float* bias,
                                 float* y, int B, int D, int H, int W, int Co, int out_ncdhw, void* stream) {
     MIC_REQUIRE(x0 && Wk && y && (C1 == 0 || x1), "conv3_tc_fwd: null pointer");
