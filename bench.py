@@ -310,7 +310,7 @@ def run_ours(args):
 
     # --- per-kernel pass (CUDA events around every C-ABI launch, same steps) -> roofline of the dominant kernel
     roofline, shares = None, None
-    if rank == 0 and not args.no_kernel_pass:
+    if rank == 0 and world == 1 and not args.no_kernel_pass:      # N = 1 only: the pass steps the model on this rank alone
         peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
@@ -346,7 +346,7 @@ def run_ours(args):
     # --- BASELINE.json's second metric: the cross-modal attention kernel in isolation (config 4: 4096 windows of 343
     #     tokens, 96 channels, 3 heads of 32; fp32 I/O, TF32 tensor cores), timed alone with CUDA events
     attn = None
-    if rank == 0 and not args.no_kernel_pass and not args.no_attn_isolation:
+    if rank == 0 and world == 1 and not args.no_kernel_pass and not args.no_attn_isolation:
         from micformer_b200 import ops as _ops
         torch.cuda.empty_cache()
         Bw, Ca, Ha = 4096, 96, 3

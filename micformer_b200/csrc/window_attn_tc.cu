@@ -496,6 +496,32 @@ __device__ __forceinline__ void softmax_block(uint32_t taddr, int nch, int valid
     l_out = l;
 }
 
+// Single-pass variant for a row whose shift mb is known up front (see the Cauchy-Schwarz bound in the kernel): every chunk
+// is read from TMEM exactly once.  Chunk 0 may already sit in va.
+__device__ __forceinline__ float exp_block(uint32_t taddr, int nch, int valid, float sc, float mb, uint32_t (&va)[32],
+                                           uint32_t (&vb)[32], bool va_loaded) {
+    float l = 0.f;
+    if (!va_loaded) {
+        tld32_nowait(taddr, va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    for (int c = 0; c < nch; c += 2) {
+        if (c + 1 < nch) tld32_nowait(taddr + (uint32_t)((c + 1) * 32), vb);
+        l += chunk_exp(va, sc, mb, valid - c * 32);
+        tst32(taddr + (uint32_t)(c * 32), va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (c + 1 < nch) {
+            if (c + 2 < nch) tld32_nowait(taddr + (uint32_t)((c + 2) * 32), va);
+            l += chunk_exp(vb, sc, mb, valid - (c + 1) * 32);
+            tst32(taddr + (uint32_t)((c + 1) * 32), vb);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+    }
+    return l;
+}
+
 __global__ void __launch_bounds__(A2_THREADS, 1)
 window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapV, AttnTcArgs a) {
     extern __shared__ uint8_t at_raw[];
@@ -508,6 +534,7 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     uint64_t* p_full = s_full + 2;             // [2] 128 arrivals
     uint64_t* o_full = p_full + 2;             // [2]
     uint32_t* tslot = reinterpret_cast<uint32_t*>(o_full + 2);
+    float* kmax2 = reinterpret_cast<float*>(tslot + 2);   // [AT_SLOTS][2]: max_j |k_j|^2 of the K tile in a slot (per conditioning warp)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmt = (a.N + 127) / 128;
@@ -668,15 +695,46 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
             // ---- block 0: keys [0, 192), all valid
             abar_wait(&s_full[x], 0u);                // two s_full phases per tile: parities 0, 1
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float m0, l0;
-            softmax_block(sbase, A2_B0 / 32, A2_B0, -INFINITY, a.scale_log2, m0, l0, va, vb);
+            // Softmax is invariant to the shift m; it only has to keep exp2 in range.  s_ij <= |q_i| max_j |k_j|
+            // (Cauchy-Schwarz) is known without reading S, so when that bound is within 2^64 of an actual score of the
+            // row (taken from the first chunk), the max pass is skipped and S is read from TMEM ONCE.  Otherwise (norms
+            // far above the scores) the warp takes the exact two-pass path for this tile.
+            float bound;
+            {
+                const uint8_t* qrow = ring + (size_t)((3 * j) % AT_SLOTS) * AT_SLOT_BYTES + (size_t)(mt * 128 + r) * 128;
+                float q2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 t = *reinterpret_cast<const float4*>(qrow + c * 16);
+                    q2 += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+                }
+                const int ks = (3 * j + 1) % AT_SLOTS;
+                bound = sqrtf(q2 * fmaxf(kmax2[2 * ks], kmax2[2 * ks + 1])) * 1.0001f;
+            }
+            const float mbB = bound * a.scale_log2;
+            tld32_nowait(sbase, va);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float mest = chunk_max(va, -INFINITY, 32);
+            const bool row_live = mt * 128 + r < a.N;
+            const bool fast = __all_sync(0xffffffffu, !row_live || (mbB - mest * a.scale_log2 <= 64.f));
+            float m0, l0, m1, l1;
+            if (fast) {
+                l0 = exp_block(sbase, A2_B0 / 32, A2_B0, a.scale_log2, mbB, va, vb, true);
+                m0 = bound;
+            } else {
+                softmax_block(sbase, A2_B0 / 32, A2_B0, -INFINITY, a.scale_log2, m0, l0, va, vb);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             abar_arrive(&p_full[x]);
             // ---- block 1: keys [192, N)
             abar_wait(&s_full[x], 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float m1, l1;
-            softmax_block(sbase, nch1, v1, m0, a.scale_log2, m1, l1, va, vb);
+            if (fast) {
+                l1 = exp_block(sbase, nch1, v1, a.scale_log2, mbB, va, vb, false);
+                m1 = bound;
+            } else {
+                softmax_block(sbase, nch1, v1, m0, a.scale_log2, m1, l1, va, vb);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             abar_arrive(&p_full[x]);
             const float mb0 = m0 * a.scale_log2, mb1 = m1 * a.scale_log2;
@@ -720,12 +778,30 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
             const int s = (int)(u % AT_SLOTS);
             abar_wait(&full[s], (uint32_t)((u / AT_SLOTS) & 1));
             uint4* p4 = reinterpret_cast<uint4*>(ring + s * AT_SLOT_BYTES);
-#pragma unroll 8
-            for (int i = et; i < nvec; i += 64) {
-                uint4 t = p4[i];
-                t.x = (t.x + 0x1000u) & 0xFFFFE000u; t.y = (t.y + 0x1000u) & 0xFFFFE000u;
-                t.z = (t.z + 0x1000u) & 0xFFFFE000u; t.w = (t.w + 0x1000u) & 0xFFFFE000u;
-                p4[i] = t;
+            const bool is_k = u % 3 == 1;
+            float nmax = 0.f;                        // largest squared row norm seen by this thread's 8-lane groups
+#pragma unroll 4
+            for (int i0 = 0; i0 < nvec; i0 += 64) {
+                const int i = i0 + et;               // float4 index: row = i >> 3 (8 consecutive lanes share a row)
+                float sq = 0.f;
+                if (i < nvec) {
+                    uint4 t = p4[i];
+                    t.x = (t.x + 0x1000u) & 0xFFFFE000u; t.y = (t.y + 0x1000u) & 0xFFFFE000u;
+                    t.z = (t.z + 0x1000u) & 0xFFFFE000u; t.w = (t.w + 0x1000u) & 0xFFFFE000u;
+                    p4[i] = t;
+                    const float a0 = __uint_as_float(t.x), a1 = __uint_as_float(t.y), a2 = __uint_as_float(t.z), a3 = __uint_as_float(t.w);
+                    sq = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                }
+                if (is_k) {
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                    nmax = fmaxf(nmax, sq);
+                }
+            }
+            if (is_k) {
+                nmax = warp_max(nmax);
+                if (lane == 0) kmax2[2 * s + (warp - 10)] = nmax;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             abar_arrive(&rdy[s]);
