@@ -50,6 +50,19 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// t -> (t / d, t % d).  Linear indices of this model fit 32 bits; 64-bit division is a ~100-instruction software routine,
+// so take the hardware-friendly 32-bit path whenever the value allows it (warp-uniform in practice).
+__device__ __forceinline__ void divmod(int64_t& t, int d, int& r) {
+    if ((uint64_t)t <= 0xFFFFFFFFull) {
+        const uint32_t q = (uint32_t)t / (uint32_t)d;
+        r = (int)((uint32_t)t - q * (uint32_t)d);
+        t = q;
+    } else {
+        r = (int)(t % d);
+        t /= d;
+    }
+}
+
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- programmatic dependent launch (PDL).  Every kernel is launched with the programmatic-stream-serialization

@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(256) offset_head_fwd_kernel(const float* __res
             o0 = fmaf(a, sw[c], o0); o1 = fmaf(a, sw[HC + c], o1); o2 = fmaf(a, sw[2 * HC + c], o2);
         }
         int64_t t = p;
-        const int x = (int)(t % Wp); t /= Wp;
-        const int y = (int)(t % Hp); t /= Hp;
-        const int z = (int)(t % Dp);
+        int x; divmod(t, Wp, x);
+        int y; divmod(t, Hp, y);
+        int z; divmod(t, Dp, z);
         float r[3];
         ref_point(z, y, x, Dp, Hp, Wp, r);
         pos[p * 3 + 0] = o0 + r[0];
@@ -155,12 +155,13 @@ __global__ void __launch_bounds__(256) deform_sample_fwd_kernel(const float* __r
     const int C4 = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        const int64_t p = idx / C4;
+        int64_t pq = idx;
+        int c4; divmod(pq, C4, c4);
+        const int64_t p = pq;
         int64_t t = p;
-        const int x = (int)(t % g.Wp); t /= g.Wp;
-        const int y = (int)(t % g.Hp); t /= g.Hp;
-        const int z = (int)(t % g.Dp); t /= g.Dp;
+        int x; divmod(t, g.Wp, x);
+        int y; divmod(t, g.Hp, y);
+        int z; divmod(t, g.Dp, z);
         const int b = (int)t;
         const float cz = sample_coord(z, pos[p * 3 + 0], g.Dp);
         const float cy = sample_coord(y, pos[p * 3 + 1], g.Hp);
@@ -193,12 +194,13 @@ __global__ void __launch_bounds__(256) deform_sample_bwd_kernel(const float* __r
     const int C4 = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        const int64_t p = idx / C4;
+        int64_t pq = idx;
+        int c4; divmod(pq, C4, c4);
+        const int64_t p = pq;
         int64_t t = p;
-        const int x = (int)(t % g.Wp); t /= g.Wp;
-        const int y = (int)(t % g.Hp); t /= g.Hp;
-        const int z = (int)(t % g.Dp); t /= g.Dp;
+        int x; divmod(t, g.Wp, x);
+        int y; divmod(t, g.Hp, y);
+        int z; divmod(t, g.Dp, z);
         const int b = (int)t;
         const float cz = sample_coord(z, pos[p * 3 + 0], g.Dp);
         const float cy = sample_coord(y, pos[p * 3 + 1], g.Hp);

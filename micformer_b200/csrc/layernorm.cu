@@ -10,10 +10,14 @@ struct LnGeom {
 };
 
 __device__ __forceinline__ bool padded_to_row(const LnGeom& g, int64_t prow, int64_t& row) {
+    if (g.Dp == g.D && g.Hp == g.H && g.Wp == g.W) {     // no trailing pad (every window-2 layer): identity
+        row = prow;
+        return true;
+    }
     int64_t t = prow;
-    const int x = (int)(t % g.Wp); t /= g.Wp;
-    const int y = (int)(t % g.Hp); t /= g.Hp;
-    const int z = (int)(t % g.Dp); t /= g.Dp;
+    int x; divmod(t, g.Wp, x);
+    int y; divmod(t, g.Hp, y);
+    int z; divmod(t, g.Dp, z);
     if (x >= g.W || y >= g.H || z >= g.D) return false;
     row = ((t * g.D + z) * g.H + y) * (int64_t)g.W + x;
     return true;

@@ -16,13 +16,14 @@ __global__ void __launch_bounds__(256) block_permute_kernel(const float* __restr
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         int64_t t = idx;
-        const int l = (int)(t % LV) * VEC; t /= LV;
-        const int ky = (int)(t % k); t /= k;
-        const int kz = (int)(t % k); t /= k;
+        int lq; divmod(t, LV, lq);
+        const int l = lq * VEC;
+        int ky; divmod(t, k, ky);
+        int kz; divmod(t, k, kz);
         const int64_t r = t;                      // row index
-        const int wx = (int)(t % Wq); t /= Wq;
-        const int hy = (int)(t % Hq); t /= Hq;
-        const int dz = (int)(t % Dq); t /= Dq;
+        int wx; divmod(t, Wq, wx);
+        int hy; divmod(t, Hq, hy);
+        int dz; divmod(t, Dq, dz);
         const int64_t b = t;
         const int64_t goff = b * grid_batch_stride +
                              ((((int64_t)dz * k + kz) * (Hq * k) + (hy * k + ky)) * (int64_t)(Wq * k) + (int64_t)wx * k) * C + l;
@@ -132,12 +133,12 @@ __global__ void __launch_bounds__(256) crop_residual_kernel(const float* __restr
     pdl_sync();
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C4);
-        int64_t t = idx / C4;
+        int64_t t = idx;
+        int c; divmod(t, C4, c);
         const int64_t row = t;
-        const int x = (int)(t % W); t /= W;
-        const int yy = (int)(t % H); t /= H;
-        const int z = (int)(t % D); t /= D;
+        int x; divmod(t, W, x);
+        int yy; divmod(t, H, yy);
+        int z; divmod(t, D, z);
         const int64_t prow = ((t * Dp + z) * Hp + yy) * (int64_t)Wp + x;
         const float s = rowscale ? rowscale[t] : 1.f;
         const float4 r = reinterpret_cast<const float4*>(res)[row * C4 + c];
@@ -153,12 +154,12 @@ __global__ void __launch_bounds__(256) crop_residual_bwd_kernel(const float* __r
     pdl_sync();
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C4);
-        int64_t t = idx / C4;
+        int64_t t = idx;
+        int c; divmod(t, C4, c);
         const int64_t prow = t;
-        const int x = (int)(t % Wp); t /= Wp;
-        const int yy = (int)(t % Hp); t /= Hp;
-        const int z = (int)(t % Dp); t /= Dp;
+        int x; divmod(t, Wp, x);
+        int yy; divmod(t, Hp, yy);
+        int z; divmod(t, Dp, z);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (x < W && yy < H && z < D) {
             const int64_t row = ((t * D + z) * H + yy) * (int64_t)W + x;

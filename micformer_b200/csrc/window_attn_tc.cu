@@ -705,7 +705,8 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
                 float q2 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const float4 t = *reinterpret_cast<const float4*>(qrow + c * 16);
+                    // rows are 128 B apart: start each lane at a different 16-byte column (sum order is irrelevant)
+                    const float4 t = *reinterpret_cast<const float4*>(qrow + (((c + lane) & 7) << 4));
                     q2 += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
                 }
                 const int ks = (3 * j + 1) % AT_SLOTS;
