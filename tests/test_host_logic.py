@@ -59,3 +59,13 @@ def test_reference_arm_prints_the_contract_line():
     out2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                            "--size", "64", "--batch", "1"], capture_output=True, text=True, env=dict(env, RANK="1"), timeout=120)
     assert out2.returncode == 0 and out2.stdout.strip() == ""
+
+
+def test_fused_tail_algebra_design_artifact():
+    """scripts/fused_tail_algebra.py: the composed ConvTranspose(k4,s4) o Conv3d(k3) weights planned for the decoder tail
+     reproduce torch's two convolutions, including the bias at the volume border."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fused_tail_algebra as A
+    for seed, dims in [(0, (3, 4, 5)), (1, (1, 2, 1)), (2, (2, 2, 2))]:
+        err, nz = A.check(seed=seed, dims=dims)
+        assert err < 1e-12 and nz == 216
