@@ -522,6 +522,13 @@ __device__ __forceinline__ float exp_block(uint32_t taddr, int nch, int valid, f
     return l;
 }
 
+// ISSUERS = 1: warp 0 is the TMA producer and warp 1 issues the MMAs of both pipelines (the validated round-1 kernel).
+// ISSUERS = 2 (opt-in, MICFORMER_ATTN_ISSUERS=2): one issuing thread per pipeline -- a K=8 TF32 tcgen05.mma costs its
+// issuing thread ~100 clocks whatever N is (profiles/r01_ubench_b200.txt), and the 51 MMAs per tile of both pipelines on
+// one thread are about half of the kernel's time.  Warp 0 lane 0 then drives pipeline 0 AND the TMA loads (both are
+// non-blocking polls), warp 1 lane 0 drives pipeline 1, and the operand slots are released by per-tile commits counted by
+// the `empty` barriers (nmt arrivals) instead of by counters private to a single issuer.
+template <int ISSUERS>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapV, AttnTcArgs a) {
     extern __shared__ uint8_t at_raw[];
@@ -548,7 +555,7 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < AT_SLOTS; ++s) { abar_init(&full[s], 1); abar_init(&empty[s], 1); abar_init(&rdy[s], 64); }
+        for (int s = 0; s < AT_SLOTS; ++s) { abar_init(&full[s], 1); abar_init(&empty[s], ISSUERS == 1 ? 1 : nmt); abar_init(&rdy[s], 64); }
         for (int x = 0; x < 2; ++x) { abar_init(&s_full[x], 1); abar_init(&p_full[x], 128); abar_init(&o_full[x], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -562,6 +569,98 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     const uint32_t tmem = *tslot;
     pdl_sync();            // prologue above (ring clear, barriers, TMEM) overlaps the previous kernel
 
+    if (ISSUERS == 2 && warp <= 1) {
+        if (lane == 0) {
+            // ---- one issuing thread per pipeline; warp 0's thread also feeds the TMA ring
+            const int x = warp;
+            const uint32_t idesc_s0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(A2_B0 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_s1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(w1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) |
+                                     ((uint32_t)(128 >> 4) << 24);
+            const int ks_pv1 = (v1 + 7) / 8;
+            const uint32_t ring_a = asmem(ring);
+            const uint32_t tcol = tmem + (uint32_t)(x * A2_PIPE_COLS);
+            auto slot_addr = [&](int u) { return ring_a + (uint32_t)(u % AT_SLOTS) * AT_SLOT_BYTES; };
+            auto issue_s = [&](int j, int mt, int h) {
+                const uint32_t qa = slot_addr(3 * j), ka = slot_addr(3 * j + 1);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = adesc(qa + (uint32_t)(mt * 128 * 128 + ks * 32), 16, 1024, 2);
+                    const uint64_t bd = adesc(ka + (uint32_t)(h * A2_B0 * 128 + ks * 32), 16, 1024, 2);
+                    amma_ss(tcol, ad, bd, h ? idesc_s1 : idesc_s0, ks ? 1u : 0u);
+                }
+                acommit(&s_full[x]);
+            };
+            auto issue_pv = [&](int j, int h) {
+                const uint32_t ocol = tcol + (uint32_t)(A2_B0 + 32 * h);
+                const int n = h ? ks_pv1 : A2_B0 / 8;
+                uint64_t bd = adesc(slot_addr(3 * j + 2) + (uint32_t)(h * (A2_B0 / 8) * 1024), 4096, 512, 1);
+                for (int kk = 0; kk < n; ++kk, bd += 1024 >> 4)
+                    amma_ts(ocol, tcol + (uint32_t)(kk * 8), bd, idesc_o, kk ? 1u : 0u);
+            };
+            if (x == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQK) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+            }
+            const int n_loads = x == 0 ? (int)(3 * nit) : 0;
+            int u_load = 0;                               // next slot use to load (item u_load / 3, part u_load % 3)
+            int j = 0, mt = x;                            // nmt >= 2: tile g = x is (item 0, tile x)
+            int64_t g = x;
+            int st = g < G ? 0 : 3;
+            uint32_t pw = 0;
+            while (st != 3 || u_load < n_loads) {
+                if (u_load < n_loads) {
+                    const int s = u_load % AT_SLOTS;
+                    if (abar_test(&empty[s], (uint32_t)((u_load / AT_SLOTS) & 1) ^ 1u)) {
+                        const int part = u_load % 3;
+                        const uint32_t it = blockIdx.x + (uint32_t)(u_load / 3) * gridDim.x;
+                        const uint32_t head = it % (uint32_t)a.heads;
+                        uint32_t w = it / (uint32_t)a.heads;
+                        const uint32_t wx = w % (uint32_t)a.nww; w /= (uint32_t)a.nww;
+                        const uint32_t wy = w % (uint32_t)a.nwh; w /= (uint32_t)a.nwh;
+                        const uint32_t wz = w % (uint32_t)a.nwd; w /= (uint32_t)a.nwd;
+                        abar_expect(&full[s], box_bytes);
+                        tma_load_5d(ring + s * AT_SLOT_BYTES, part == 2 ? &mapV : &mapQK, &full[s], part * a.C + (int)head * 32,
+                                    (int)(wx * a.ww), (int)(wy * a.wh), (int)(wz * a.wd), (int)w);
+                        ++u_load;
+                    }
+                }
+                if (st == 3) continue;
+                const int u0 = 3 * j;
+                if (st == 0) {
+                    if (abar_test(&rdy[u0 % AT_SLOTS], (uint32_t)((u0 / AT_SLOTS) & 1)) &&
+                        abar_test(&rdy[(u0 + 1) % AT_SLOTS], (uint32_t)(((u0 + 1) / AT_SLOTS) & 1))) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_s(j, mt, 0);
+                        st = 1;
+                    }
+                } else if (st == 1) {
+                    if (abar_test(&p_full[x], pw & 1u) &&
+                        abar_test(&rdy[(u0 + 2) % AT_SLOTS], (uint32_t)(((u0 + 2) / AT_SLOTS) & 1))) {
+                        ++pw;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_pv(j, 0);
+                        issue_s(j, mt, 1);
+                        acommit(&empty[u0 % AT_SLOTS]);               // one of the nmt releases of Q and K
+                        acommit(&empty[(u0 + 1) % AT_SLOTS]);
+                        st = 2;
+                    }
+                } else {
+                    if (abar_test(&p_full[x], pw & 1u)) {
+                        ++pw;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_pv(j, 1);
+                        acommit(&o_full[x]);
+                        acommit(&empty[(u0 + 2) % AT_SLOTS]);         // one of the nmt releases of V
+                        g += 2;
+                        mt += 2;
+                        if (mt >= nmt) { mt -= nmt; ++j; }
+                        st = g < G ? 0 : 3;
+                    }
+                }
+            }
+        }
+    } else
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQK) : "memory");
@@ -869,12 +968,16 @@ int tc_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, 
     if (grid > a.items) grid = a.items;
     static const bool force_v1 = getenv("MICFORMER_ATTN_V1") != nullptr;
     if (N > A2_B0 && !force_v1) {
+        static const bool two_issuers = []() { const char* v = getenv("MICFORMER_ATTN_ISSUERS"); return v && v[0] == '2'; }();
         static bool attr2 = false;
         if (!attr2) {
-            cudaFuncSetAttribute(window_attn_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(window_attn_tc2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(window_attn_tc2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr2 = true;
         }
-        mic::launch(window_attn_tc2_fwd_kernel, dim3((unsigned)grid), dim3(A2_THREADS), smem, st, mQK, mV, a);
+        if (a.items >= ((int64_t)1 << 30)) return MIC_ERR_UNSUPPORTED;
+        if (two_issuers) mic::launch(window_attn_tc2_fwd_kernel<2>, dim3((unsigned)grid), dim3(A2_THREADS), smem, st, mQK, mV, a);
+        else mic::launch(window_attn_tc2_fwd_kernel<1>, dim3((unsigned)grid), dim3(A2_THREADS), smem, st, mQK, mV, a);
         return check_launch("window_attn_tc2_fwd_kernel");
     }
     mic::launch(window_attn_tc_fwd_kernel, dim3((unsigned)grid), dim3(AT_THREADS), smem, st, mQK, mV, a);
