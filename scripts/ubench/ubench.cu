@@ -146,6 +146,81 @@ __global__ void mma_rate_kernel(int N, int nmma, int rotate, int a_from_tmem, lo
     tmem_free(tmem, warp);
 }
 
+
+// ---- 2b. several issuing threads (one per warp), each accumulating into its own TMEM tile: is the ~100-clock floor of a
+// K=8 TF32 MMA per issuing thread or per SM?  kind_f16 = 1 issues kind::f16 (bf16 operands, K=16 per instruction) instead.
+__global__ void mma_multi_kernel(int N, int nmma, int issuers, int kind_f16, long long* out) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bar[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (4096 + 256 * 32) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t tmem = tmem_alloc_all(&slot, warp);
+    long long dt = 0;
+    if (lane == 0 && warp < issuers) {
+        const uint32_t a_addr = s32(sm), b_addr = s32(sm + 4096);
+        const uint64_t ad = desc_noswz(a_addr, 16 * 128, 128);
+        const uint64_t bd = desc_noswz(b_addr, (N / 8) * 128, 128);
+        // kind::tf32: a/b format 2 (tf32) at bits 7/10; kind::f16: format 1 (bf16)
+        const uint32_t fmt = kind_f16 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t d = tmem + (uint32_t)(warp * 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; ++i) {
+            if (kind_f16)
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(i ? 1u : 0u) : "memory");
+            else
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(i ? 1u : 0u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar[warp])) : "memory");
+        asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D2;\nbra W2;\nD2:\n}\n"
+                     ::"r"(s32(&bar[warp])), "r"(0) : "memory");
+        dt = clock64() - t0;
+        out[warp] = dt;
+    }
+    tmem_free(tmem, warp);
+}
+
+// ---- 3b. the conv3_tc producer's exact pattern: lane pairs fetch the two 16-byte halves of one 32-byte sector (8 channels
+// of a position); lanes_per_pos = 2 (32 B per position) or 4 (64 B per position)
+__global__ void cpasync_pair_kernel(const float* __restrict__ src, int64_t stride_floats, int lanes_per_pos, int groups,
+                                    long long* out) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int tid = threadIdx.x;
+    const uint32_t sbase = s32(sm);
+    auto issue = [&](int g) {
+        for (int k = 0; k < 3; ++k) {
+            const int e = (g * 3 + k) * blockDim.x + tid;
+            const int pos = e / lanes_per_pos, part = e % lanes_per_pos;
+            const float* p = src + (int64_t)pos * stride_floats + 4 * part;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, 16;" ::"r"(sbase + (uint32_t)((e % 2048) * 16)), "l"(p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncthreads();
+    const long long t0 = clock64();
+    int issued = 0;
+    for (; issued < 5 && issued < groups; ++issued) issue(issued);
+    for (int g = 0; g < groups; ++g) {
+        asm volatile("cp.async.wait_group 4;" ::: "memory");
+        if (issued < groups) issue(issued++);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const long long t1 = clock64();
+    if (tid == 0) out[0] = t1 - t0;
+}
+
 // ---- 3. cp.async gathers.  bytes_per_thread 16 or 32; groups in flight: 1 (latency) or 5
 __global__ void cpasync_kernel(const float* __restrict__ src, int64_t stride_floats, int per_thread16, int groups, int depth,
                                long long* out) {
@@ -217,6 +292,20 @@ int main() {
                        rot ? "rotating accumulators" : "one accumulator      ", (double)h[0] / nm, (double)h[1] / nm,
                        128.0 * N * 8 / ((double)h[0] / nm));
             }
+    printf("== tcgen05.mma issue floor vs number of issuing threads (one per warp, own TMEM tile each): cycles per MMA per issuer\n");
+    CK(cudaFuncSetAttribute(mma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    for (int f16 = 0; f16 < 2; ++f16)
+        for (int N : {16, 32, 96})
+            for (int issuers : {1, 2, 4}) {
+                const int nm = 256;
+                long long hh[4] = {0, 0, 0, 0};
+                CK(cudaMemset(out, 0, 64));
+                mma_multi_kernel<<<1, 128, 4096 + 256 * 32 + 1024>>>(N, nm, issuers, f16, out);
+                CK(cudaDeviceSynchronize()); CK(cudaMemcpy(hh, out, 32, cudaMemcpyDeviceToHost));
+                long long mx = 0; for (int i = 0; i < issuers; ++i) mx = hh[i] > mx ? hh[i] : mx;
+                printf("  %s N=%3d, %d issuer(s): %7.1f cycles/MMA per issuer -> %6.0f MAC/clk per SM\n", f16 ? "kind::f16 (K=16)" : "kind::tf32 (K=8)",
+                       N, issuers, (double)mx / nm, issuers * 128.0 * N * (f16 ? 16 : 8) / ((double)mx / nm));
+            }
     printf("== cp.async 16 B gathers, 128 threads x 3 elements per group, 192 B stride (L2-resident source)\n");
     float* src; CK(cudaMalloc(&src, (size_t)64 << 20)); CK(cudaMemset(src, 0, (size_t)64 << 20));
     CK(cudaFuncSetAttribute(cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
@@ -227,6 +316,14 @@ int main() {
             printf("  %2d B per element, %d group(s) in flight: %7.1f cycles per group (%d elements)\n", 16 * b16, depth,
                    (double)h[0] / groups, 3 * 128);
         }
+    printf("== cp.async, conv3_tc producer pattern (lane groups share a position), 5 groups in flight\n");
+    CK(cudaFuncSetAttribute(cpasync_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (int lpp : {2, 4}) {
+        const int groups = 64;
+        for (int rep = 0; rep < 2; ++rep) { cpasync_pair_kernel<<<1, 128, 40960>>>(src, 48, lpp, groups, out); get(); }
+        printf("  %d lanes (%2d B) per position: %7.1f cycles per group of %d positions = %5.1f B/clk per CTA\n", lpp, 16 * lpp,
+               (double)h[0] / groups, 384 / lpp, 384.0 * 16 / ((double)h[0] / groups));
+    }
     printf("== fence.proxy.async.shared::cta after a shared store\n");
     for (int threads : {32, 128, 256}) { fence_kernel<<<1, threads>>>(200, out); get(); printf("  %3d threads: %6.1f cycles per (store + fence)\n", threads, (double)h[0] / 200); }
     return 0;
