@@ -1,1 +1,1 @@
-from .dice import MDiceLoss  # noqa: F401
+from .dice import MDiceLoss, MDiceLoss_Val  # noqa: F401

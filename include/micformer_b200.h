@@ -34,8 +34,12 @@ const char* mic_last_error_string(void);
 /* number of kernel launches issued by this library in the calling process since load / last reset */
 int64_t mic_launch_count(void);
 void mic_reset_launch_count(void);
-/* 0 = fp32 CUDA-core GEMMs (exact parity path), 1 = tcgen05 TF32 tensor-core GEMMs where shapes allow
- * (fp32 in/out, operands read as tf32, fp32 accumulate in TMEM), 2 = reserved (3xTF32 split; currently == 0) */
+/* 0 = fp32 CUDA-core GEMMs / convs / attention everywhere (exact parity path);
+ * 1 = tcgen05 tensor-core kernels where shapes allow (fp32 in/out, fp32 accumulate in TMEM): forward GEMMs run the
+ *     3xTF32 split (fp32-faithful), backward GEMMs and the 3x3x3 convs single-pass TF32 with operands rounded to nearest;
+ *     GEMM shapes the tensor-core kernel declines run the fp32 CUDA-core kernel of mode 0 and are reported once per
+ *     entry point on stderr (MICFORMER_WARN_FALLBACK=0 silences it);
+ * 2 = accepted and treated as 0 (kept for ABI stability). */
 int mic_set_gemm_mode(int mode);
 int mic_get_gemm_mode(void);
 
@@ -146,6 +150,15 @@ int mic_dice_bce_finalize(const double* sums, float* loss, float* coef /*[C*3]*/
                           void* stream);
 int mic_dice_bce_bwd(const float* logits, const float* target, const float* coef, const float* dloss, float* dlogits,
                      int B, int C, int64_t S, double n_per_channel, void* stream);
+/* the same with uint8 / bool one-hot labels (what dataset/MMWHS.py:392,414-425 produces before the script's .float()):
+ * the loss reads 1 byte per label instead of 4 */
+int mic_dice_bce_partial_u8(const float* logits, const uint8_t* target, double* sums, int B, int C, int64_t S, void* stream);
+int mic_dice_bce_bwd_u8(const float* logits, const uint8_t* target, const float* coef, const float* dloss, float* dlogits,
+                        int B, int C, int64_t S, void* stream);
+/* loss = (w_dice * sum_c dice_c + w_bce * sum_c bce_c) / C.  (0.7, 0.3) is MDiceLoss (loss/dice.py:158-166) ==
+ * mic_dice_bce_finalize; (1, 0) is MDiceLoss_Val (loss/dice.py:216-221). */
+int mic_dice_bce_finalize_weighted(const double* sums, float* loss, float* coef /*[C*3]*/, int C, double n_per_channel,
+                                   double w_dice, double w_bce, void* stream);
 
 /* ---- Multi-tensor Adam (torch.optim.Adam(lr, betas, eps, weight_decay), train_mmwhs_noPad.py:114,201) over all
  *      parameter tensors in one launch.  params/grads/exp_avg/exp_avg_sq: device arrays of n_tensors pointers (a null

@@ -44,6 +44,9 @@ SIGNATURES = {
     "mic_dice_bce_partial": [P, P, P, I, I, L, P],
     "mic_dice_bce_finalize": [P, P, P, I, D, P],
     "mic_dice_bce_bwd": [P, P, P, P, P, I, I, L, D, P],
+    "mic_dice_bce_partial_u8": [P, P, P, I, I, L, P],
+    "mic_dice_bce_bwd_u8": [P, P, P, P, P, I, I, L, P],
+    "mic_dice_bce_finalize_weighted": [P, P, P, I, D, D, D, P],
     "mic_adam_chunk_elems": [],
     "mic_adam_step": [P, P, P, P, P, P, P, I, I, P, P, F, F, F, F, P],
     "mic_crop_residual": [P, P, P, P, I, I, I, I, I, I, I, I, P],
@@ -130,6 +133,8 @@ COST = {
     "mic_block_permute": lambda a: (0, 8 * a[2] * a[3] * a[4] * a[5] * a[6] ** 3 * a[7]),
     "mic_dice_bce_partial": lambda a: (0, 8 * a[3] * a[4] * a[5]),
     "mic_dice_bce_bwd": lambda a: (0, 12 * a[5] * a[6] * a[7]),
+    "mic_dice_bce_partial_u8": lambda a: (0, 5 * a[3] * a[4] * a[5]),
+    "mic_dice_bce_bwd_u8": lambda a: (0, 9 * a[5] * a[6] * a[7]),
     "mic_offset_head_fwd": lambda a: (0, 4 * _prod(*a[5:9]) * (a[9] + 3)),
     "mic_offset_head_bwd": lambda a: (0, 4 * _prod(*a[9:13]) * (2 * a[13] + 3)),
     "mic_crop_residual": lambda a: (0, 12 * _prod(*a[4:8]) * a[11]),
@@ -214,9 +219,20 @@ def call(name: str, *args):
     _invoke(name, args, False)
 
 
+_declined = set()
+
+
 def try_call(name: str, *args) -> bool:
-    """Like ``call`` but returns False when the entry point declines the shape (MIC_ERR_UNSUPPORTED)."""
-    return _invoke(name, args, True)
+    """Like ``call`` but returns False when the entry point declines the shape (MIC_ERR_UNSUPPORTED); the caller then
+    runs the exact fp32 CUDA-core kernel.  Reported once per entry point (MICFORMER_WARN_FALLBACK=0 silences it)."""
+    ok = _invoke(name, args, True)
+    if not ok and name not in _declined:
+        _declined.add(name)
+        if os.environ.get("MICFORMER_WARN_FALLBACK", "1") != "0":
+            import warnings
+            warnings.warn(f"micformer_b200: {name} declined a shape ({last_error()}); using the fp32 CUDA-core kernel "
+                          f"(reported once per entry point)", RuntimeWarning, stacklevel=3)
+    return ok
 
 
 def check_cuda_f32(*tensors):

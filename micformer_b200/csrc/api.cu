@@ -48,6 +48,19 @@ int simt_window_attn_bwd(const float*, int, const float*, const float*, int, con
 using namespace mic;
 
 namespace mic {
+// Tensor-core mode: a shape the tcgen05 kernel declines runs the exact fp32 CUDA-core kernel instead.  That is correct but
+// slow, so it is reported once per entry point on stderr (MICFORMER_WARN_FALLBACK=0 silences it).
+void warn_fallback(const char* op, int a, int b, int c) {
+    static const bool on = []() { const char* v = getenv("MICFORMER_WARN_FALLBACK"); return !(v && v[0] == '0'); }();
+    if (!on) return;
+    static std::atomic<unsigned> seen{0};
+    unsigned h = 0;
+    for (const char* p = op; *p; ++p) h = h * 31u + (unsigned)*p;
+    const unsigned bit = 1u << (h % 32u);
+    if (seen.fetch_or(bit) & bit) return;
+    fprintf(stderr, "[micformer_b200] %s: shape (%d, %d, %d) is not taken by the tcgen05 kernel; using the fp32 CUDA-core "
+                    "kernel (reported once per entry point)\n", op, a, b, c);
+}
 bool pdl_enabled() {
     static const bool on = []() { const char* v = getenv("MICFORMER_PDL"); return !(v && v[0] == '0'); }();
     return on;
@@ -75,6 +88,7 @@ extern "C" int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
         int rc = tc_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
                                rows_per_sample, accumulate, mode, (cudaStream_t)stream);
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
+        warn_fallback("mic_linear_fwd", M, N, K);
     }
     return simt_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
                            rows_per_sample, accumulate, (cudaStream_t)stream);
@@ -89,6 +103,7 @@ extern "C" int mic_linear_bwd_data(const float* dY, int lddy, const float* W, in
         int rc = tc_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
                                     accumulate, mode, (cudaStream_t)stream);
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
+        warn_fallback("mic_linear_bwd_data", M, N, K);
     }
     return simt_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
                                 accumulate, (cudaStream_t)stream);
@@ -103,6 +118,7 @@ extern "C" int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, 
         int rc = tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample, mode,
                                       (cudaStream_t)stream);
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
+        warn_fallback("mic_linear_bwd_weight", M, N, K);
     }
     return simt_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample,
                                   (cudaStream_t)stream);

@@ -38,23 +38,33 @@ __global__ void __launch_bounds__(256) block_permute_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------ loss
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// TT = float (one-hot float labels, what train_mmwhs_noPad.py:181 hands over after .float()) or uint8_t (the bool / uint8
+// one-hot the dataset produces, dataset/MMWHS.py:392,414-425, read without the 4x wider float copy)
+template <typename TT>
 __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restrict__ logits,
-                                                           const float* __restrict__ target,
+                                                           const TT* __restrict__ target,
                                                            double* __restrict__ sums, int C, int64_t S) {
     pdl_sync();
     // grid: (chunks, B*C); one (b,c) slab per blockIdx.y
     const int64_t slab = blockIdx.y;
     const int c = (int)(slab % C);
     const float* lg = logits + slab * S;
-    const float* tg = target + slab * S;
+    const TT* tg = target + slab * S;
     float s_pt = 0.f, s_pp = 0.f, s_tt = 0.f, s_ce = 0.f;
     const int64_t S4 = S >> 2;
-    const bool vec = aligned16(lg) && aligned16(tg);
+    const bool vec = aligned16(lg) && (reinterpret_cast<uintptr_t>(tg) & (4 * sizeof(TT) - 1)) == 0;
     if (vec) {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S4; i += (int64_t)gridDim.x * blockDim.x) {
             const float4 x = reinterpret_cast<const float4*>(lg)[i];
-            const float4 t = reinterpret_cast<const float4*>(tg)[i];
-            const float xs[4] = {x.x, x.y, x.z, x.w}, ts[4] = {t.x, t.y, t.z, t.w};
+            float ts[4];
+            if (sizeof(TT) == 4) {
+                const float4 t = reinterpret_cast<const float4*>(tg)[i];
+                ts[0] = t.x; ts[1] = t.y; ts[2] = t.z; ts[3] = t.w;
+            } else {
+                const uchar4 t = reinterpret_cast<const uchar4*>(tg)[i];
+                ts[0] = t.x ? 1.f : 0.f; ts[1] = t.y ? 1.f : 0.f; ts[2] = t.z ? 1.f : 0.f; ts[3] = t.w ? 1.f : 0.f;
+            }
+            const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float p = sigmoidf_(xs[k]);
@@ -66,7 +76,7 @@ __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restri
     for (int64_t i = (vec ? S4 * 4 : 0) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float p = sigmoidf_(lg[i]);
-        const float t = tg[i];
+        const float t = sizeof(TT) == 4 ? (float)tg[i] : (tg[i] ? 1.f : 0.f);
         s_pt = fmaf(p, t, s_pt); s_pp = fmaf(p, p, s_pp); s_tt = fmaf(t, t, s_tt);
         s_ce += (t - 1.f) * fmaxf(log1pf(-p), -100.f) - t * fmaxf(logf(p), -100.f);
     }
@@ -87,8 +97,10 @@ __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restri
     }
 }
 
+// loss = (w_dice * sum_c dice_c + w_bce * sum_c bce_c) / C: (0.7, 0.3) = MDiceLoss (loss/dice.py:158-166), (1, 0) = MDiceLoss_Val
+// (loss/dice.py:216-221)
 __global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __restrict__ loss, float* __restrict__ coef,
-                                     int C, double n) {
+                                     int C, double n, double w_dice, double w_bce) {
     pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double dice = 0.0, ce = 0.0;
@@ -98,14 +110,15 @@ __global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __r
         dice += 1.0 - (2.0 * I + 1.0) / den;
         ce += B / n;
         // d loss / d p = a*t + b*p + e*(p-t)/max(p(1-p),1e-12)
-        coef[c * 3 + 0] = (float)(-2.0 * 0.7 / (C * den));
-        coef[c * 3 + 1] = (float)(0.7 * 2.0 * (2.0 * I + 1.0) / (C * den * den));
-        coef[c * 3 + 2] = (float)(0.3 / (C * n));
+        coef[c * 3 + 0] = (float)(-2.0 * w_dice / (C * den));
+        coef[c * 3 + 1] = (float)(w_dice * 2.0 * (2.0 * I + 1.0) / (C * den * den));
+        coef[c * 3 + 2] = (float)(w_bce / (C * n));
     }
-    *loss = (float)((0.7 * dice + 0.3 * ce) / C);
+    *loss = (float)((w_dice * dice + w_bce * ce) / C);
 }
 
-__global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+template <typename TT>
+__global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits, const TT* __restrict__ target,
                                                        const float* __restrict__ coef, const float* __restrict__ dloss,
                                                        float* __restrict__ dlogits, int C, int64_t S) {
     pdl_sync();
@@ -114,11 +127,11 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
     const float g = dloss ? *dloss : 1.f;
     const float a = coef[c * 3] * g, b = coef[c * 3 + 1] * g, e = coef[c * 3 + 2] * g;
     const float* lg = logits + slab * S;
-    const float* tg = target + slab * S;
+    const TT* tg = target + slab * S;
     float* dl = dlogits + slab * S;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
         const float p = sigmoidf_(lg[i]);
-        const float t = tg[i];
+        const float t = sizeof(TT) == 4 ? (float)tg[i] : (tg[i] ? 1.f : 0.f);
         const float q = p * (1.f - p);
         const float dp = a * t + b * p + e * (p - t) / fmaxf(q, 1e-12f);
         dl[i] = dp * q;
@@ -198,34 +211,66 @@ extern "C" int mic_block_permute(const float* src, float* dst, int B, int Dq, in
     return check_launch("block_permute_kernel");
 }
 
-extern "C" int mic_dice_bce_partial(const float* logits, const float* target, double* sums, int B, int C, int64_t S,
-                                    void* stream) {
+static int dice_partial_launch(const float* logits, const void* target, int target_u8, double* sums, int B, int C, int64_t S,
+                               void* stream) {
     MIC_REQUIRE(logits && target && sums && B > 0 && C > 0 && S > 0, "dice_bce_partial: bad arguments");
     int chunks = (int)ceil_div64(S, 256 * 16);
     const int cap = ceil_div(num_sms() * 8, B * C);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    mic::launch(dice_partial_kernel, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits, target, sums, C, S);
+    if (target_u8)
+        mic::launch(dice_partial_kernel<uint8_t>, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits,
+                    (const uint8_t*)target, sums, C, S);
+    else
+        mic::launch(dice_partial_kernel<float>, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits,
+                    (const float*)target, sums, C, S);
     return check_launch("dice_partial_kernel");
 }
 
-extern "C" int mic_dice_bce_finalize(const double* sums, float* loss, float* coef, int C, double n_per_channel,
-                                     void* stream) {
-    MIC_REQUIRE(sums && loss && coef && C > 0 && n_per_channel > 0, "dice_bce_finalize: bad arguments");
-    mic::launch(dice_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, loss, coef, C, n_per_channel);
-    return check_launch("dice_finalize_kernel");
+extern "C" int mic_dice_bce_partial(const float* logits, const float* target, double* sums, int B, int C, int64_t S,
+                                    void* stream) {
+    return dice_partial_launch(logits, target, 0, sums, B, C, S, stream);
+}
+extern "C" int mic_dice_bce_partial_u8(const float* logits, const uint8_t* target, double* sums, int B, int C, int64_t S,
+                                       void* stream) {
+    return dice_partial_launch(logits, target, 1, sums, B, C, S, stream);
 }
 
-extern "C" int mic_dice_bce_bwd(const float* logits, const float* target, const float* coef, const float* dloss,
-                                float* dlogits, int B, int C, int64_t S, double n_per_channel, void* stream) {
-    (void)n_per_channel;
+extern "C" int mic_dice_bce_finalize_weighted(const double* sums, float* loss, float* coef, int C, double n_per_channel,
+                                              double w_dice, double w_bce, void* stream) {
+    MIC_REQUIRE(sums && loss && coef && C > 0 && n_per_channel > 0, "dice_bce_finalize: bad arguments");
+    mic::launch(dice_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, loss, coef, C, n_per_channel, w_dice,
+                w_bce);
+    return check_launch("dice_finalize_kernel");
+}
+extern "C" int mic_dice_bce_finalize(const double* sums, float* loss, float* coef, int C, double n_per_channel,
+                                     void* stream) {
+    return mic_dice_bce_finalize_weighted(sums, loss, coef, C, n_per_channel, 0.7, 0.3, stream);
+}
+
+static int dice_bwd_launch(const float* logits, const void* target, int target_u8, const float* coef, const float* dloss,
+                           float* dlogits, int B, int C, int64_t S, void* stream) {
     MIC_REQUIRE(logits && target && coef && dlogits && B > 0 && C > 0 && S > 0, "dice_bce_bwd: bad arguments");
     int chunks = (int)ceil_div64(S, 256 * 8);
     const int cap = ceil_div(num_sms() * 16, B * C);
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    mic::launch(dice_bwd_kernel, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits, target, coef, dloss, dlogits, C, S);
+    if (target_u8)
+        mic::launch(dice_bwd_kernel<uint8_t>, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits,
+                    (const uint8_t*)target, coef, dloss, dlogits, C, S);
+    else
+        mic::launch(dice_bwd_kernel<float>, dim3(chunks, B * C), dim3(256), 0, (cudaStream_t)stream, logits,
+                    (const float*)target, coef, dloss, dlogits, C, S);
     return check_launch("dice_bwd_kernel");
+}
+extern "C" int mic_dice_bce_bwd(const float* logits, const float* target, const float* coef, const float* dloss,
+                                float* dlogits, int B, int C, int64_t S, double n_per_channel, void* stream) {
+    (void)n_per_channel;
+    return dice_bwd_launch(logits, target, 0, coef, dloss, dlogits, B, C, S, stream);
+}
+extern "C" int mic_dice_bce_bwd_u8(const float* logits, const uint8_t* target, const float* coef, const float* dloss,
+                                   float* dlogits, int B, int C, int64_t S, void* stream) {
+    return dice_bwd_launch(logits, target, 1, coef, dloss, dlogits, B, C, S, stream);
 }
 
 extern "C" int mic_crop_residual(const float* res, const float* branch, const float* rowscale, float* y, int B, int D,

@@ -522,8 +522,9 @@ __device__ __forceinline__ float exp_block(uint32_t taddr, int nch, int valid, f
     return l;
 }
 
-// ISSUERS = 1: warp 0 is the TMA producer and warp 1 issues the MMAs of both pipelines (the validated round-1 kernel).
-// ISSUERS = 2 (opt-in, MICFORMER_ATTN_ISSUERS=2): one issuing thread per pipeline -- a K=8 TF32 tcgen05.mma costs its
+// ISSUERS = 1 (MICFORMER_ATTN_ISSUERS=1): warp 0 is the TMA producer and warp 1 issues the MMAs of both pipelines.
+// ISSUERS = 2 (default since round 2: 1.449 -> 1.155 ms on config 4, gpurun_out r2a; all window-attention parity tests pass
+// with it): one issuing thread per pipeline -- a K=8 TF32 tcgen05.mma costs its
 // issuing thread ~100 clocks whatever N is (profiles/r01_ubench_b200.txt), and the 51 MMAs per tile of both pipelines on
 // one thread are about half of the kernel's time.  Warp 0 lane 0 then drives pipeline 0 AND the TMA loads (both are
 // non-blocking polls), warp 1 lane 0 drives pipeline 1, and the operand slots are released by per-tile commits counted by
@@ -968,7 +969,7 @@ int tc_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, 
     if (grid > a.items) grid = a.items;
     static const bool force_v1 = getenv("MICFORMER_ATTN_V1") != nullptr;
     if (N > A2_B0 && !force_v1) {
-        static const bool two_issuers = []() { const char* v = getenv("MICFORMER_ATTN_ISSUERS"); return v && v[0] == '2'; }();
+        static const bool two_issuers = []() { const char* v = getenv("MICFORMER_ATTN_ISSUERS"); return !(v && v[0] == '1'); }();
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(window_attn_tc2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

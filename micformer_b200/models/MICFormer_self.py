@@ -536,19 +536,15 @@ class MicFormer(nn.Module):
         return wr, br64
 
     def forward(self, moving, fixed):
-        """Reference signature: two (B,1,D,H,W) volumes -> (B, E/2, D, H, W) features (M:992-1039)."""
+        """Reference signature: two (B,1,D,H,W) volumes -> (B, E/2, D, H, W) features (M:992-1039), any embed_dim.
+        ``Head`` does not come through here: it fuses this tail with ``out_conv`` (``ops.SegHeadFn``)."""
         vol = torch.cat([moving, fixed], dim=1).contiguous()
+        if vol.dtype != torch.float32:
+            vol = vol.float()
         m, f = self._trunk(vol)
         wr, br64 = self._tail_params()
-        E = self.embed_dim
-        Ch = E // 2
-        # identity 1x1 "conv" is not available; reuse the seg-head op with an identity centre tap
-        wo = torch.zeros(27, Ch, Ch, device=vol.device)
-        wo[13] = torch.eye(Ch, device=vol.device)
-        if Ch > 16:
-            raise NotImplementedError("MicFormer.forward stand-alone needs E/2 <= 16; use Head (fused tail) instead")
-        bo = torch.zeros(Ch, device=vol.device)
-        return ops.SegHeadFn.apply(m, f, self.norm2.weight, self.norm2.bias, wr, br64, wo, None, bo)
+        y = ops.UnpatchFn.apply(m, f, self.norm2.weight, self.norm2.bias, wr, br64)      # channels-last
+        return y.permute(0, 4, 1, 2, 3).contiguous()                                      # NCDHW like the reference
 
 
 class Head(nn.Module):

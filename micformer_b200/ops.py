@@ -695,6 +695,41 @@ class PatchExpandFn(torch.autograd.Function):
         return dx, dW, db8, dnw, dnb
 
 
+class UnpatchFn(torch.autograd.Function):
+    """The tail of ``MicFormer.forward`` on its own (reference M:1033-1037): cat[moving, fixed] -> norm2 ->
+    ConvTranspose3d(2E->E/2,k4,s4), emitted channels-last (B, 4D, 4H, 4W, E/2); any E.  ``Head`` uses ``SegHeadFn``
+    (this plus out_conv) instead.  wr: (2E, 64*E/2) permuted (kz,ky,kx,co); br64: bias tiled 64x."""
+
+    @staticmethod
+    def forward(ctx, xm, xf, n2w, n2b, wr, br64):
+        N.check_cuda_f32(xm, xf, n2w, n2b, wr, br64)
+        B, D, H, W, E = xm.shape
+        T = B * D * H * W
+        Ch = wr.shape[1] // 64
+        xn, mean, rstd = ln_fwd(xm, xf, n2w, n2b, (B, D, H, W))
+        rows = linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True)
+        y = _empty((B, 4 * D, 4 * H, 4 * W, Ch), xm)
+        block_permute(rows, y, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
+        ctx.save_for_backward(xm, xf, n2w, mean, rstd, xn, wr)
+        ctx.meta = (B, D, H, W, E, Ch)
+        ctx.n2b = n2b
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xm, xf, n2w, mean, rstd, xn, wr = ctx.saved_tensors
+        B, D, H, W, E, Ch = ctx.meta
+        T = B * D * H * W
+        dy = dy.contiguous()
+        drows = _empty((T, 64 * Ch), xm)
+        block_permute(dy, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
+        dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
+        dwr, dbr64 = linear_bwd_weight(drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
+        dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W), beta=ctx.n2b)
+        return dxm, dxf, dn2w, dn2b, dwr, dbr64
+
+
 class SegHeadFn(torch.autograd.Function):
     """Decoder tail (reference M:1033-1037 + Head M:1053): cat[moving, fixed] -> norm2 -> ConvTranspose3d(2E->E/2,k4,s4)
     -> Conv3d(E/2->num_classes,k3,p1), NCDHW logits.  wr: (2E, 64*E/2) permuted (kz,ky,kx,co); br64: bias tiled 64x;
@@ -751,26 +786,40 @@ class SegHeadFn(torch.autograd.Function):
 
 class DiceBceLossFn(torch.autograd.Function):
     """MDiceLoss.forward (reference loss/dice.py:158-166) in one reduction pass + closed-form backward.
+    ``target``: float32 one-hot (the reference contract) or uint8 / bool one-hot (read as bytes, no float copy).
     ``group`` (a torch.distributed process group or None): all-reduce the 4*C partial sums so that the Dice
-    terms span the GLOBAL batch; None keeps the reference's per-process semantics."""
+    terms span the GLOBAL batch; None keeps the reference's per-process semantics.
+    ``w_dice``, ``w_bce``: (0.7, 0.3) for MDiceLoss, (1, 0) for MDiceLoss_Val (loss/dice.py:216-221).
+
+    With a process group the backward yields d(global loss)/d(local logits); data-parallel gradient averaging
+    (GradSync, 1/world) must then be replaced by a SUM -- ``MDiceLoss.grad_reduce`` says which."""
 
     @staticmethod
-    def forward(ctx, logits, target, group, world):
-        N.check_cuda_f32(logits, target)
+    def forward(ctx, logits, target, group, world, w_dice=0.7, w_bce=0.3):
+        N.check_cuda_f32(logits)
         if logits.shape != target.shape:
             raise RuntimeError(f"MDiceLoss: logits {tuple(logits.shape)} vs target {tuple(target.shape)}")
+        u8 = target.dtype in (torch.uint8, torch.bool)
+        if not u8 and target.dtype != torch.float32:
+            raise RuntimeError(f"MDiceLoss: target dtype {target.dtype} (float32, uint8 or bool one-hot expected)")
+        if not (target.is_cuda and target.is_contiguous()):
+            raise RuntimeError("MDiceLoss: target must be a contiguous CUDA tensor")
         B, C = logits.shape[:2]
         S = logits[0, 0].numel()
         sums = torch.zeros(C * 4, device=logits.device, dtype=torch.float64)
-        N.call("mic_dice_bce_partial", N.ptr(logits), N.ptr(target), N.ptr(sums), B, C, S)
+        if u8:
+            N.call("mic_dice_bce_partial_u8", N.ptr(logits), N.ptr(target), N.ptr(sums), B, C, S)
+        else:
+            N.call("mic_dice_bce_partial", N.ptr(logits), N.ptr(target), N.ptr(sums), B, C, S)
         n = float(B * S)
         if group is not None and world > 1:
             torch.distributed.all_reduce(sums, group=group)
             n *= world
         loss = _empty((), logits)
         coef = _empty((C * 3,), logits)
-        N.call("mic_dice_bce_finalize", N.ptr(sums), N.ptr(loss), N.ptr(coef), C, n)
+        N.call("mic_dice_bce_finalize_weighted", N.ptr(sums), N.ptr(loss), N.ptr(coef), C, n, float(w_dice), float(w_bce))
         ctx.save_for_backward(logits, target, coef)
+        ctx.u8 = u8
         ctx.n = n
         return loss
 
@@ -782,8 +831,11 @@ class DiceBceLossFn(torch.autograd.Function):
         S = logits[0, 0].numel()
         dl = torch.empty_like(logits)
         dloss = dloss.contiguous().float()
-        N.call("mic_dice_bce_bwd", N.ptr(logits), N.ptr(target), N.ptr(coef), N.ptr(dloss), N.ptr(dl), B, C, S, ctx.n)
-        return dl, None, None, None
+        if ctx.u8:
+            N.call("mic_dice_bce_bwd_u8", N.ptr(logits), N.ptr(target), N.ptr(coef), N.ptr(dloss), N.ptr(dl), B, C, S)
+        else:
+            N.call("mic_dice_bce_bwd", N.ptr(logits), N.ptr(target), N.ptr(coef), N.ptr(dloss), N.ptr(dl), B, C, S, ctx.n)
+        return dl, None, None, None, None, None
 
 
 class DeformSampleFn(torch.autograd.Function):

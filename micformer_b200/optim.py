@@ -22,6 +22,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables = None
         self._grad_ptrs_host = None
         self._lr_on_device = None
+        self._stage_busy = None        # event: the last non-blocking H2D copy of the pinned grad-pointer table
         self.arena = None
 
     def attach_arena(self, arena) -> None:
@@ -34,6 +35,14 @@ class FusedAdam(torch.optim.Optimizer):
             self.arena.zero()
             return
         super().zero_grad(set_to_none=set_to_none)
+
+    def load_state_dict(self, state_dict) -> None:
+        """torch.optim.Adam checkpoints (and our own) load here; the device tables that cache raw pointers of the moment
+        buffers and the step counters are rebuilt from the loaded state on the next ``step()`` / ``set_lr()``."""
+        super().load_state_dict(state_dict)
+        self._tables = None
+        self._grad_ptrs_host = None
+        self._lr_on_device = None
 
     # ---- state in torch.optim.Adam's layout --------------------------------------------------------------
     def _init_state(self):
@@ -50,8 +59,11 @@ class FusedAdam(torch.optim.Optimizer):
             if "exp_avg" not in st:
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            else:                                          # loaded from a torch.optim.Adam checkpoint
-                self._steps[i] = float(st["step"])
+            else:                                          # loaded from a torch.optim.Adam checkpoint (or our own)
+                self._steps[i] = float(st.get("step", 0.0))
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if st[k].device != p.device or st[k].dtype != torch.float32 or not st[k].is_contiguous():
+                        st[k] = st[k].to(device=p.device, dtype=torch.float32).contiguous()
             st["step"] = self._steps[i]                    # 0-dim view into the device counters
         chunk = N.load().mic_adam_chunk_elems()
         ct, ci = [], []
@@ -79,8 +91,13 @@ class FusedAdam(torch.optim.Optimizer):
             for p in self._params:
                 if p.grad is not None:
                     N.check_cuda_f32(p.grad)
+            if self._stage_busy is not None:
+                self._stage_busy.synchronize()      # the previous async copy must have read the pinned table
             self._grad_stage.copy_(torch.tensor(ptrs, dtype=torch.int64))
             t["grads"].copy_(self._grad_stage, non_blocking=True)
+            if not torch.cuda.is_current_stream_capturing():
+                self._stage_busy = torch.cuda.Event()
+                self._stage_busy.record()
             self._grad_ptrs_host = ptrs
         lr = float(g["lr"])
         if lr != self._lr_on_device:

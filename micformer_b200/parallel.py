@@ -16,13 +16,17 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None, arena=None):
+    def __init__(self, params, bucket_bytes: int = 64 << 20, process_group=None, arena=None, reduce: str = "mean"):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.group = process_group
         self._plan = None      # list of lists of param indices
         self._flat = None
         self.arena = arena     # GradArena: the gradients already live in one flat buffer -> one in-place all-reduce
+        if reduce not in ("mean", "sum"):
+            raise ValueError("GradSync: reduce must be 'mean' (per-rank loss, the reference semantics) or 'sum' "
+                             "(MDiceLoss(process_group=...): the loss already spans the global batch)")
+        self.reduce = reduce
 
     @property
     def world(self) -> int:
@@ -50,30 +54,38 @@ class GradSync:
         p0 = self.params[0]
         self._flat = [torch.empty(sum(self.params[i].numel() for i in b), device=p0.device, dtype=p0.dtype) for b in plan]
 
+    def _reduce_(self, flat: torch.Tensor, async_op: bool = False):
+        """in-place mean (or sum, ``reduce="sum"``: a loss that already spans the global batch) over the ranks.  NCCL
+        averages inside the collective (ReduceOp.AVG): no separate 1/world pass over the 247 MB buffer."""
+        if self.reduce == "sum":
+            return dist.all_reduce(flat, group=self.group, async_op=async_op)
+        if dist.get_backend(self.group) == "nccl":
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        flat.mul_(1.0 / self.world)                      # gloo has no AVG
+        return dist.all_reduce(flat, group=self.group, async_op=async_op)
+
     def sync(self) -> None:
         """Average ``.grad`` across ranks in place.  Call after ``backward()``."""
         if self.world <= 1:
             return
         if self.arena is not None and self.arena.attached():
             # parameters without a gradient (concat_back_dim.0) hold zeros on every rank: harmless to include
-            self.arena.flat.mul_(1.0 / self.world)
-            dist.all_reduce(self.arena.flat, group=self.group)
+            self._reduce_(self.arena.flat)
             return
         if self._plan is None:
             self._build_plan()
         works = []
-        inv = 1.0 / self.world
         for flat, idxs in zip(self._flat, self._plan):
             grads = [self.params[i].grad for i in idxs]
             views = list(torch.split(flat, [g.numel() for g in grads]))
             torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
-            flat.mul_(inv)
-            works.append(dist.all_reduce(flat, group=self.group, async_op=True))
+            works.append(self._reduce_(flat, async_op=True))
         for w, flat, idxs in zip(works, self._flat, self._plan):
             w.wait()
             grads = [self.params[i].grad for i in idxs]
             views = list(torch.split(flat, [g.numel() for g in grads]))
-            torch._foreach_copy_([g.reshape(-1) if g.is_contiguous() else g for g in grads], views)
+            for g, v in zip(grads, views):
+                g.copy_(v.view(g.shape))                # handles non-contiguous .grad too
 
     def skipped(self) -> List[int]:
         live = set(i for b in (self._plan or []) for i in b)
