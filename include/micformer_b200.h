@@ -171,6 +171,32 @@ int mic_adam_step(void* params, void* grads, void* exp_avg, void* exp_avg_sq, co
                   const int* chunk_tensor, const int* chunk_index, int n_chunks, int n_tensors, float* steps,
                   const float* lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* ---- Fused block kernels for small channel counts (the train config's stage 0: C = 48, 8-token windows).  GEMM operands
+ *      are "split bf16": x = hi + lo (two bf16 roundings), products hi*hi + lo*hi + hi*lo on tcgen05 kind::f16 with fp32
+ *      accumulation in TMEM (~2^-17 relative, tighter than TF32).  Weights are consumed as pre-swizzled shared-memory
+ *      IMAGES produced by mic_weight_images: B operand of N rows x K reduction elements, K-major bf16, SWIZZLE_128B,
+ *      panels of 64 k (n_pad rows x 128 B each), rows >= N / k >= K zero.
+ *      jobs: device array of n_jobs records of 9 x int64 {src fp32 ptr, hi ptr, lo ptr, ld, N, K, transpose, n_pad,
+ *      k_panels} with B[n][k] = transpose ? src[k*ld + n] : src[n*ld + k]; max_chunks = max over jobs of
+ *      k_panels*n_pad*8 (grid sizing). */
+int mic_weight_images(const void* jobs, int n_jobs, int64_t max_chunks, void* stream);
+/* y = x + rowscale[row / rows_per_sample] * (fc2(GELU(fc1(LayerNorm(x)))))  -- Mlp.forward inside the residual (reference
+ * M:28-34, 403-404 / 516-524, DropPath scale M:419-424); x, y (T, C).  w1 image: N = 4C (n_pad 4C), K = C; w2 image:
+ * N = C (n_pad = C rounded up to 16), K = 4C.  C in {24, 48}; other sizes return MIC_ERR_UNSUPPORTED. */
+int mic_mlp_block_fwd(const float* x, float* y, const float* gamma, const float* beta, const float* b1, const float* b2,
+                      const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo, const float* rowscale,
+                      int rows_per_sample, int T, int C, float eps, void* stream);
+/* Backward of the same from dy and x alone (LayerNorm, fc1, GELU are recomputed on chip): dx (T, C) is written,
+ * dW1 (4C, C), db1 (4C), dW2 (C, 4C), db2 (C), dgamma (C), dbeta (C) are accumulated atomically (caller-zeroed or running
+ * sums).  Images: w1nk = fc1 as N = 4C rows (n_pad: 4C rounded up to 64) x K = C; w2kn = fc2 transposed, same shape;
+ * w1kn = fc1 transposed as N = C rows (n_pad: C rounded up to 16) x K = 4C. */
+int mic_mlp_block_bwd(const float* dy, const float* x, float* dx, const float* gamma, const float* beta, const float* b1,
+                      const void* w1nk_hi, const void* w1nk_lo, const void* w2kn_hi, const void* w2kn_lo,
+                      const void* w1kn_hi, const void* w1kn_lo, const float* rowscale, int rows_per_sample, float* dW1,
+                      float* db1, float* dW2, float* db2, float* dgamma, float* dbeta, int T, int C, float eps, void* stream);
+/* dynamic shared memory the fused MLP kernels need for this C (-1: not built) */
+int mic_mlp_block_smem(int C);
+
 /* ---- small utilities: y = a + rowscale*b with crop from a padded grid (residual after window_reverse + crop
  *      :397-400,:419), fill, axpy ---- */
 int mic_crop_residual(const float* res, const float* branch, const float* rowscale, float* y, int B, int D, int H,

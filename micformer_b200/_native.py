@@ -49,6 +49,10 @@ SIGNATURES = {
     "mic_dice_bce_finalize_weighted": [P, P, P, I, D, D, D, P],
     "mic_adam_chunk_elems": [],
     "mic_adam_step": [P, P, P, P, P, P, P, I, I, P, P, F, F, F, F, P],
+    "mic_weight_images": [P, I, L, P],
+    "mic_mlp_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, F, P],
+    "mic_mlp_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, F, P],
+    "mic_mlp_block_smem": [I],
     "mic_crop_residual": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "mic_crop_residual_bwd": [P, P, P, I, I, I, I, I, I, I, I, P],
 }
@@ -137,12 +141,16 @@ COST = {
     "mic_dice_bce_bwd_u8": lambda a: (0, 9 * a[5] * a[6] * a[7]),
     "mic_offset_head_fwd": lambda a: (0, 4 * _prod(*a[5:9]) * (a[9] + 3)),
     "mic_offset_head_bwd": lambda a: (0, 4 * _prod(*a[9:13]) * (2 * a[13] + 3)),
+    "mic_mlp_block_fwd": lambda a: (16 * a[12] * a[13] * a[13], 8 * a[12] * a[13] + 4 * 8 * a[13] * a[13]),
+    "mic_mlp_block_bwd": lambda a: (40 * a[20] * a[21] * a[21], 12 * a[20] * a[21] + 4 * 16 * a[21] * a[21]),
     "mic_crop_residual": lambda a: (0, 12 * _prod(*a[4:8]) * a[11]),
     "mic_crop_residual_bwd": lambda a: (0, 4 * a[3] * (_prod(*a[4:7]) + _prod(*a[7:10])) * a[10]),
 }
 
 
 TAG = {
+    "mic_mlp_block_fwd": lambda a: f"T{a[12]}xC{a[13]}",
+    "mic_mlp_block_bwd": lambda a: f"T{a[20]}xC{a[21]}",
     "mic_linear_fwd": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",
     "mic_linear_bwd_data": lambda a: f"M{a[7]}xN{a[8]}xK{a[9]}",
     "mic_linear_bwd_weight": lambda a: f"M{a[8]}xN{a[9]}xK{a[10]}",

@@ -1,0 +1,154 @@
+"""Host side of the fused tcgen05 block kernels (``csrc/block_mlp*.cu``, ``csrc/block_attn*.cu``).
+
+The fused kernels read their weights as pre-swizzled bf16 hi/lo shared-memory IMAGES (``include/micformer_b200.h``,
+"Fused block kernels").  ``WeightImages`` owns the image buffer of one module's weights and the job records that
+``mic_weight_images`` turns into images; ``refresh_all`` converts every registered module of a model in ONE launch
+(the parameters change every optimizer step, so the model refreshes once per forward; a block used stand-alone
+refreshes its own images).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+FUSED_C = (24, 48)           # channel counts the fused kernels are built for
+
+
+def enabled() -> bool:
+    """fused kernels are part of the tensor-core mode (gemm mode 1); MICFORMER_FUSED=0 keeps the unfused tcgen05 path"""
+    import os
+    return N.get_gemm_mode() == 1 and os.environ.get("MICFORMER_FUSED", "1") != "0"
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class WeightImages:
+    """Images of a fixed list of weight views.  spec: (name, tensor, N, K, transpose, n_pad) with the image being the B
+    operand B[n][k] = transpose ? W[k][n] : W[n][k] of a row-major fp32 weight ``tensor`` (leading dimension = its row
+    stride)."""
+
+    def __init__(self, specs: Sequence[Tuple[str, torch.Tensor, int, int, bool, int]]):
+        self.specs = list(specs)
+        dev = self.specs[0][1].device
+        off = 0
+        self.offsets = {}
+        rows = []
+        self.max_chunks = 0
+        for name, t, n, k, tr, n_pad in self.specs:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.stride(-1) == 1):
+                raise RuntimeError("WeightImages: weights must be CUDA float32 with a unit inner stride")
+            panels = (k + 63) // 64
+            nbytes = panels * n_pad * 128
+            self.offsets[name] = (off, off + nbytes, nbytes)        # hi offset, lo offset, bytes per image
+            rows.append([t.data_ptr(), off, off + nbytes, t.stride(0), n, k, int(tr), n_pad, panels])
+            self.max_chunks = max(self.max_chunks, panels * n_pad * 8)
+            off += 2 * nbytes
+        self.buf = torch.empty(_ceil(off, 256), dtype=torch.uint8, device=dev)
+        base = self.buf.data_ptr()
+        for r in rows:
+            r[1] += base
+            r[2] += base
+        self.jobs_host = rows
+        self.jobs = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self._ptrs = [t.data_ptr() for _, t, *_ in self.specs]
+        self.stamp = -1          # model-level refresh counter this buffer was last converted at
+
+    def valid(self) -> bool:
+        return [t.data_ptr() for _, t, *_ in self.specs] == self._ptrs
+
+    def hi(self, name: str) -> int:
+        return self.buf.data_ptr() + self.offsets[name][0]
+
+    def lo(self, name: str) -> int:
+        return self.buf.data_ptr() + self.offsets[name][1]
+
+    def refresh(self) -> None:
+        N.call("mic_weight_images", N.ptr(self.jobs), len(self.jobs_host), self.max_chunks)
+
+
+def refresh_all(images: List[WeightImages]) -> None:
+    """one launch for the images of all ``images`` (they must live on one device)"""
+    if not images:
+        return
+    key = tuple(id(i) for i in images)
+    cache = refresh_all._cache
+    ent = cache.get(key)
+    if ent is None:
+        jobs = torch.cat([i.jobs for i in images], dim=0).contiguous()
+        ent = cache[key] = (jobs, max(i.max_chunks for i in images), images)
+        if len(cache) > 8:
+            cache.pop(next(iter(cache)))
+    jobs, mc, _ = ent
+    N.call("mic_weight_images", N.ptr(jobs), jobs.shape[0], mc)
+
+
+refresh_all._cache = {}
+
+
+def mlp_images(fc1_w: torch.Tensor, fc2_w: torch.Tensor) -> WeightImages:
+    """fc1 (4C, C), fc2 (C, 4C) -> the four images the fused MLP kernels read (forward: w1_nk, w2_nk; backward adds the
+    transposed views w2_kn, w1_kn)."""
+    hid, c = fc1_w.shape
+    cp = _ceil(c, 16)
+    hp = _ceil(hid, 64)                             # the backward walks the hidden axis in chunks of 64 rows
+    return WeightImages([
+        ("w1_nk", fc1_w, hid, c, False, hp),        # fc1:           B[n = hidden][k = c]      = W1[n][k]
+        ("w2_nk", fc2_w, c, hid, False, cp),        # fc2:           B[n = c][k = hidden]      = W2[n][k]
+        ("w2_kn", fc2_w, hid, c, True, hp),         # dh = dy W2:    B[n = hidden][k = c]      = W2[k][n]
+        ("w1_kn", fc1_w, c, hid, True, cp),         # dxn = dh W1:   B[n = c][k = hidden]      = W1[k][n]
+    ])
+
+
+_epoch = 0        # bumped by every model-level refresh; an image set whose stamp equals it is current
+
+
+def epoch() -> int:
+    return _epoch
+
+
+def model_refresh(images: List[WeightImages]) -> None:
+    """Called once per model forward (the optimizer changed the weights): one launch converts all images."""
+    global _epoch
+    _epoch += 1
+    if images:
+        refresh_all(images)
+        for i in images:
+            i.stamp = _epoch
+
+
+def ensure_current(img: Optional[WeightImages]) -> None:
+    """A block used stand-alone (no enclosing model refreshed this forward) converts its own images."""
+    if img is not None and img.stamp != _epoch:
+        img.refresh()
+
+
+def mlp_supported(c: int, hid: int) -> bool:
+    return enabled() and c in FUSED_C and hid == 4 * c
+
+
+def mlp_block_fwd(x: torch.Tensor, img: WeightImages, gamma, beta, b1, b2, rowscale: Optional[torch.Tensor], rps: int,
+                  eps: float) -> torch.Tensor:
+    """y = x + rowscale * fc2(GELU(fc1(LN(x))));  x (..., C) contiguous fp32"""
+    c = x.shape[-1]
+    t = x.numel() // c
+    y = torch.empty_like(x)
+    N.call("mic_mlp_block_fwd", N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta), N.ptr(b1), N.ptr(b2), img.hi("w1_nk"),
+           img.lo("w1_nk"), img.hi("w2_nk"), img.lo("w2_nk"), N.ptr(rowscale), int(rps), t, c, float(eps))
+    return y
+
+
+def mlp_block_bwd(dy: torch.Tensor, x: torch.Tensor, img: WeightImages, gamma, beta, b1, rowscale: Optional[torch.Tensor],
+                  rps: int, eps: float, dgamma, dbeta, dW1, db1, dW2, db2) -> torch.Tensor:
+    """dx = dy + d(branch)/dx; the six parameter gradients are ACCUMULATED into the given buffers."""
+    c = x.shape[-1]
+    t = x.numel() // c
+    dx = torch.empty_like(x)
+    N.call("mic_mlp_block_bwd", N.ptr(dy), N.ptr(x), N.ptr(dx), N.ptr(gamma), N.ptr(beta), N.ptr(b1), img.hi("w1_nk"),
+           img.lo("w1_nk"), img.hi("w2_kn"), img.lo("w2_kn"), img.hi("w1_kn"), img.lo("w1_kn"), N.ptr(rowscale), int(rps),
+           N.ptr(dW1), N.ptr(db1), N.ptr(dW2), N.ptr(db2), N.ptr(dgamma), N.ptr(dbeta), t, c, float(eps))
+    return dx

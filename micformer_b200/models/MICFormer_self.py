@@ -17,7 +17,7 @@ from operator import mul
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import fused, ops
 from .STN import SpatialTransformer, Re_SpatialTransformer  # noqa: F401  (re-exported like the reference, M:13)
 
 
@@ -76,6 +76,11 @@ def _block_scales(block, batch, device):
     return _drop_scale(block.drop_path, batch, device), _drop_scale(block.drop_path, batch, device)
 
 
+def _current(img):
+    fused.ensure_current(img)
+    return img
+
+
 class Mlp(nn.Module):
     """M:16-34.  Parameter container; fused as LN -> fc1 -> GELU -> fc2 -> +residual inside the block ops."""
 
@@ -91,6 +96,16 @@ class Mlp(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
+
+    def fused_images(self):
+        """bf16 weight images for the fused tcgen05 MLP kernels (None when this size / mode is not fused)."""
+        w1, w2 = self.fc1.weight, self.fc2.weight
+        if not (w1.is_cuda and fused.mlp_supported(w1.shape[1], w1.shape[0])):
+            return None
+        img = self.__dict__.get("_mic_img")
+        if img is None or not img.valid():
+            img = self.__dict__["_mic_img"] = fused.mlp_images(w1.detach(), w2.detach())
+        return img
 
     def forward(self, x):
         shape = x.shape
@@ -283,7 +298,7 @@ class CrossTransformerBlock3D(nn.Module):
             x.contiguous(), xa.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
             a.proj.bias, cw, cwk, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
-            self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
+            self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()))
 
 
 class TransformerBlock3D(nn.Module):
@@ -318,7 +333,7 @@ class TransformerBlock3D(nn.Module):
             x.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
             a.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
-            self.mlp.fc2.weight, self.mlp.fc2.bias)
+            self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()))
 
 
 class PatchMerging(nn.Module):
@@ -506,6 +521,8 @@ class MicFormer(nn.Module):
     def _trunk(self, vol):
         """Everything up to (not including) cat -> norm2 -> reverse_patch_embedding; vol is (B, 2, D, H, W)."""
         self._predraw_drop_path(vol.shape[0], vol.device)
+        # the optimizer changed the weights since the last forward: rebuild all fused-kernel weight images in one launch
+        fused.model_refresh([i for i in (m.fused_images() for m in self.modules() if isinstance(m, Mlp)) if i is not None])
         moving = self.patch_embed(vol, 0)
         fixed = self.patch_embed(vol, 1)
         feats_m, feats_f = [], []

@@ -14,6 +14,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import _native as N
+from . import fused as F_
 
 LN_EPS = 1e-5
 Tensor = torch.Tensor
@@ -354,11 +355,16 @@ def _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb=None):
     return do_p, dpw, dpb
 
 
-def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims):
+def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims, img=None):
+    """``img``: the Mlp's fused-kernel weight images -> LN + fc1 + GELU + fc2 + residual in ONE tcgen05 kernel that saves
+    nothing (the backward recomputes from x1); None -> the unfused kernels with their saved intermediates."""
     B, D, H, W = dims
     C = x1.shape[-1]
     T = B * D * H * W
     Hd = f1w.shape[0]
+    if img is not None:
+        y = F_.mlp_block_fwd(x1, img, n2w, n2b, f1b, f2b, s2, D * H * W, LN_EPS)
+        return y, (None, None, None, None, None)
     xn2, mean2, rstd2 = ln_fwd(x1, None, n2w, n2b, dims)
     hpre = _empty((T, Hd), x1)
     h = linear_fwd(xn2, C, f1w, f1b, T, Hd, C, act=True, pre=hpre)
@@ -366,7 +372,7 @@ def _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims):
     return y, (xn2, mean2, rstd2, hpre, h)
 
 
-def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims, n2b=None, f1b=None, f2b=None):
+def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims, n2b=None, f1b=None, f2b=None, img=None):
     """-> dx1 (= dy + grad through LN/MLP), dn2w, dn2b, df1w, df1b, df2w, df2b"""
     xn2, mean2, rstd2, hpre, h = saved
     B, D, H, W = dims
@@ -374,6 +380,11 @@ def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims, n2b=None, f1b=None, f2b
     T = B * D * H * W
     Hd = f1w.shape[0]
     rps = D * H * W
+    if img is not None:
+        ps = (n2w, n2b, f1w, f1b, f2w, f2b)
+        gs = [_acc(p) if _acc(p) is not None else _zeros(tuple(p.shape), x1) for p in ps]
+        dx1 = F_.mlp_block_bwd(dy, x1, img, n2w, n2b, f1b, s2, rps, LN_EPS, *gs)
+        return (dx1, *[_gret(p, g) for p, g in zip(ps, gs)])
     df2w, df2b = linear_bwd_weight_side(sb, dy, C, h, Hd, T, C, Hd, wp=f2w, bp=f2b, rowscale=s2, rps=rps)
     dh = linear_bwd_data(dy, C, f2w, T, C, Hd, gelu_pre=hpre, rowscale=s2, rps=rps)
     df1w, df1b = linear_bwd_weight_side(sb, dh, Hd, xn2, C, T, Hd, C, wp=f1w, bp=f1b)
@@ -389,7 +400,7 @@ class SelfBlockFn(torch.autograd.Function):
     norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b}, norm2.{w,b}, fc1.{w,b}, fc2.{w,b}."""
 
     @staticmethod
-    def forward(ctx, x, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b):
+    def forward(ctx, x, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, mlp_img=None):
         N.check_cuda_f32(x, n1w, qw, kvw, pw, f1w, f2w)
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
@@ -402,11 +413,12 @@ class SelfBlockFn(torch.autograd.Function):
         linear_fwd(xn_p, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
         o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
         x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
-        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims)
+        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims, mlp_img)
         ctx.save_for_backward(x, xn_p, mean1, rstd1, qkv, o_p, lse, x1, *mlp_saved, n1w, qw, kvw, pw, n2w, f1w, f2w,
                               *( [s1] if s1 is not None else []), *([s2] if s2 is not None else []))
         ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
         ctx.biases = (n1b, qb, kvb, pb, n2b, f1b, f2b)
+        ctx.mlp_img = mlp_img
         return y
 
     @staticmethod
@@ -426,7 +438,8 @@ class SelfBlockFn(torch.autograd.Function):
         P = B * pdims[0] * pdims[1] * pdims[2]
         dy = dy.contiguous()
         with zero_arena(12 * C * C + 128 * C + 4096, x), side_branch() as sb:
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b)
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b,
+                                                               ctx.mlp_img)
             do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
             dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
@@ -435,7 +448,7 @@ class SelfBlockFn(torch.autograd.Function):
             linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
-                df2b)
+                df2b, None)
 
 
 class CrossBlockFn(torch.autograd.Function):
@@ -450,7 +463,7 @@ class CrossBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xa, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cwk, cb, lnw, lnb, w3, n2w,
-                n2b, f1w, f1b, f2w, f2b):
+                n2b, f1w, f1b, f2w, f2b, mlp_img=None):
         N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
@@ -472,12 +485,13 @@ class CrossBlockFn(torch.autograd.Function):
         linear_fwd(samp, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
         o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
         x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
-        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims)
+        y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims, mlp_img)
         ctx.save_for_backward(x, xa_p, xn_p, mean1, rstd1, h16, pos, samp, qkv, o_p, lse, x1, *mlp_saved, n1w, qw, kvw,
                               pw, cw, lnw, lnb, w3, n2w, f1w, f2w, *([s1] if s1 is not None else []),
                               *([s2] if s2 is not None else []))
         ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
         ctx.biases = (n1b, qb, kvb, pb, cb, n2b, f1b, f2b)
+        ctx.mlp_img = mlp_img
         return y
 
     @staticmethod
@@ -499,7 +513,8 @@ class CrossBlockFn(torch.autograd.Function):
         HC = cw.shape[-1]
         dy = dy.contiguous()
         with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x), side_branch() as sb:
-            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b)
+            dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b,
+                                                               ctx.mlp_img)
             do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
             dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
@@ -528,7 +543,7 @@ class CrossBlockFn(torch.autograd.Function):
         else:
             dxa = dxa_p
         return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, None, _gret(cb, dcb), dlnw, dlnb, dw3,
-                dn2w, dn2b, df1w, df1b, df2w, df2b)
+                dn2w, dn2b, df1w, df1b, df2w, df2b, None)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -91,13 +91,16 @@ class FusedAdam(torch.optim.Optimizer):
             for p in self._params:
                 if p.grad is not None:
                     N.check_cuda_f32(p.grad)
-            if self._stage_busy is not None:
+            capturing = torch.cuda.is_current_stream_capturing()
+            if self._stage_busy is not None and not capturing:
                 self._stage_busy.synchronize()      # the previous async copy must have read the pinned table
             self._grad_stage.copy_(torch.tensor(ptrs, dtype=torch.int64))
             t["grads"].copy_(self._grad_stage, non_blocking=True)
-            if not torch.cuda.is_current_stream_capturing():
+            if not capturing:
                 self._stage_busy = torch.cuda.Event()
                 self._stage_busy.record()
+            else:
+                self._stage_busy = None             # a captured copy re-reads the pinned table at every replay: it stays as is
             self._grad_ptrs_host = ptrs
         lr = float(g["lr"])
         if lr != self._lr_on_device:

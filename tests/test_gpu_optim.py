@@ -92,8 +92,12 @@ def test_grad_arena_direct_accumulation_matches_autograd(mode):
         MDiceLoss()(head(x), lab).backward()
         assert arena.attached()
         gl2 = float(sum((g.double() ** 2).sum() for g in ref.values() if g is not None) ** 0.5)
-        tol = 1e-4 if mode == 0 else 2e-2          # TF32 split-R partial sums are reduced in a different order
+        # mode 0 is deterministic up to fp32 atomics order.  Mode 1: every kernel is (scripts/determinism.py: <= 5e-7 run to
+        # run), but single-pass TF32 backward operands turn that reordering noise into rounding flips, and the offset branch
+        # (d pos = differences of neighbouring voxels, scripts/grad_noise.py) amplifies them: up to 2.4e-2 run to run on
+        # conv_offset / norm1 tensors whose norm is 1e-3 of the global gradient norm, <= 2e-3 elsewhere
         for k, p in head.named_parameters():
+            tol = 1e-4 if mode == 0 else (6e-2 if ("conv_offset" in k or "norm1" in k) else 2e-2)
             if ref[k] is None:
                 assert float(p.grad.abs().max()) == 0.0, k
             else:
