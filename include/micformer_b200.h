@@ -194,6 +194,24 @@ int mic_mlp_block_bwd(const float* dy, const float* x, float* dx, const float* g
                       const void* w1nk_hi, const void* w1nk_lo, const void* w2kn_hi, const void* w2kn_lo,
                       const void* w1kn_hi, const void* w1kn_lo, const float* rowscale, int rows_per_sample, float* dW1,
                       float* db1, float* dW2, float* db2, float* dgamma, float* dbeta, int T, int C, float eps, void* stream);
+/* Attention half of a block on 2x2x2 windows (TransformerBlock3D M:473-499; CrossTransformerBlock3D M:339-401 with
+ * CrossWindowAttention3D M:179-203): x1 = x + rowscale * proj(softmax(q k^T * scale) v) with q = Wq LN(x) + bq and
+ * [k|v] = Wkv src + bkv, src = LN(x) when kvsrc is null (self block) else kvsrc (the resampled other modality, not
+ * normalised).  x, kvsrc, y (B, D, H, W, C), even D/H/W; rowscale per sample.  Images: wq / wp N = C (n_pad: C up to 16) x
+ * K = C, wkv N = 2C x K = C.  Built for (C, head_dim) in {(48,16), (48,24)}; other shapes return MIC_ERR_UNSUPPORTED. */
+int mic_attn_block_fwd(const float* x, const float* kvsrc, float* y, const float* gamma, const float* beta, const float* bq,
+                       const float* bkv, const float* bp, const void* wq_hi, const void* wq_lo, const void* wkv_hi,
+                       const void* wkv_lo, const void* wp_hi, const void* wp_lo, const float* rowscale, int B, int D, int H,
+                       int W, int C, int heads, float scale, float eps, void* stream);
+/* Backward of the same from dy (gradient w.r.t. x1), x and kvsrc alone (LayerNorm, q / kv and the attention probabilities
+ * are recomputed on chip): dx = dy + LN'(...) is written; cross blocks also write dkvsrc (T, C) (pass both kvsrc and dkvsrc
+ * or neither); dgamma, dbeta, dWq (C,C), dbq, dWkv (2C,C), dbkv, dWp (C,C), dbp are accumulated atomically.
+ * imgs: host array of 10 device pointers {wq hi, lo, wkv hi, lo (forward images), wpT hi, lo, wqT hi, lo (transposed,
+ * N = C (n_pad: C up to 16) x K = C), wkvT hi, lo (transposed, N = C x K = 2C: two 64-k panels)}. */
+int mic_attn_block_bwd(const float* x, const float* kvsrc, const float* dy, float* dx, float* dkvsrc, const float* gamma,
+                       const float* beta, const float* bq, const float* bkv, const void* const* imgs, const float* rowscale,
+                       float* dgamma, float* dbeta, float* dWq, float* dbq, float* dWkv, float* dbkv, float* dWp, float* dbp,
+                       int B, int D, int H, int W, int C, int heads, float scale, float eps, void* stream);
 /* dynamic shared memory the fused MLP kernels need for this C (-1: not built) */
 int mic_mlp_block_smem(int C);
 

@@ -152,3 +152,52 @@ def mlp_block_bwd(dy: torch.Tensor, x: torch.Tensor, img: WeightImages, gamma, b
            img.lo("w1_nk"), img.hi("w2_kn"), img.lo("w2_kn"), img.hi("w1_kn"), img.lo("w1_kn"), N.ptr(rowscale), int(rps),
            N.ptr(dW1), N.ptr(db1), N.ptr(dW2), N.ptr(db2), N.ptr(dgamma), N.ptr(dbeta), t, c, float(eps))
     return dx
+
+
+# ---------------------------------------------------------------------------------------------- attention half-block
+FUSED_ATTN = ((48, 16), (48, 24))      # (C, head_dim) the fused attention kernels are built for
+
+
+def attn_images(q_w: torch.Tensor, kv_w: torch.Tensor, p_w: torch.Tensor) -> WeightImages:
+    """q (C, C), kv (2C, C), proj (C, C) -> forward images (wq_nk, wkv_nk, wp_nk) and the transposed views of the backward"""
+    c = q_w.shape[0]
+    cp = _ceil(c, 16)
+    return WeightImages([
+        ("wq_nk", q_w, c, c, False, cp),
+        ("wkv_nk", kv_w, 2 * c, c, False, 2 * c),
+        ("wp_nk", p_w, c, c, False, cp),
+        ("wp_kn", p_w, c, c, True, cp),             # do  = dy Wp:        B[n = c_in][k = c_out] = Wp[k][n]
+        ("wq_kn", q_w, c, c, True, cp),             # dxn = dq Wq
+        ("wkv_kn", kv_w, c, 2 * c, True, cp),       # dsrc = [dk|dv] Wkv: B[n = c_in][k = 2C]
+    ])
+
+
+def attn_supported(c: int, heads: int, window, dims) -> bool:
+    return (enabled() and heads > 0 and c % heads == 0 and (c, c // heads) in FUSED_ATTN and tuple(window) == (2, 2, 2)
+            and all(d % 2 == 0 for d in dims))
+
+
+def attn_block_fwd(x: torch.Tensor, kvsrc: Optional[torch.Tensor], img: WeightImages, gamma, beta, bq, bkv, bp,
+                   rowscale: Optional[torch.Tensor], heads: int, eps: float) -> torch.Tensor:
+    """x1 = x + rowscale * proj(window_attention(q(LN x), kv(kvsrc or LN x)));  x (B, D, H, W, C)"""
+    b, d, h, w, c = x.shape
+    y = torch.empty_like(x)
+    N.call("mic_attn_block_fwd", N.ptr(x), N.ptr(kvsrc), N.ptr(y), N.ptr(gamma), N.ptr(beta), N.ptr(bq), N.ptr(bkv), N.ptr(bp),
+           img.hi("wq_nk"), img.lo("wq_nk"), img.hi("wkv_nk"), img.lo("wkv_nk"), img.hi("wp_nk"), img.lo("wp_nk"),
+           N.ptr(rowscale), b, d, h, w, c, heads, float(c // heads) ** -0.5, float(eps))
+    return y
+
+
+def attn_block_bwd(dy: torch.Tensor, x: torch.Tensor, kvsrc: Optional[torch.Tensor], img: WeightImages, gamma, beta, bq, bkv,
+                   rowscale: Optional[torch.Tensor], heads: int, eps: float, dgamma, dbeta, dWq, dbq, dWkv, dbkv, dWp, dbp):
+    """-> (dx, dkvsrc or None); the eight parameter gradients are ACCUMULATED into the given buffers."""
+    import ctypes
+    b, d, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    dsrc = torch.empty_like(x) if kvsrc is not None else None
+    names = ("wq_nk", "wkv_nk", "wp_kn", "wq_kn", "wkv_kn")
+    arr = (ctypes.c_void_p * 10)(*[f(nm) for nm in names for f in (img.hi, img.lo)])
+    N.call("mic_attn_block_bwd", N.ptr(x), N.ptr(kvsrc), N.ptr(dy), N.ptr(dx), N.ptr(dsrc), N.ptr(gamma), N.ptr(beta), N.ptr(bq),
+           N.ptr(bkv), ctypes.cast(arr, ctypes.c_void_p), N.ptr(rowscale), N.ptr(dgamma), N.ptr(dbeta), N.ptr(dWq), N.ptr(dbq),
+           N.ptr(dWkv), N.ptr(dbkv), N.ptr(dWp), N.ptr(dbp), b, d, h, w, c, heads, float(c // heads) ** -0.5, float(eps))
+    return dx, dsrc

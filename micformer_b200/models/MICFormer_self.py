@@ -81,6 +81,28 @@ def _current(img):
     return img
 
 
+def _attn_images(attn):
+    """bf16 weight images of a (Cross)WindowAttention3D's q / kv / proj for the fused attention kernels (cached)"""
+    qw, kvw, pw = attn.q.weight, attn.kv.weight, attn.proj.weight
+    if not qw.is_cuda:
+        return None
+    img = attn.__dict__.get("_mic_img")
+    if img is None or not img.valid():
+        img = attn.__dict__["_mic_img"] = fused.attn_images(qw.detach(), kvw.detach(), pw.detach())
+    return img
+
+
+def _fused_block_images(block, attn, dims):
+    """(attention images, MLP images) when BOTH halves of this block run as fused kernels for this geometry, else None"""
+    C = block.dim
+    if not fused.attn_supported(C, block.num_heads, block.window_size, dims):
+        return None
+    mimg = block.mlp.fused_images()
+    if mimg is None or attn.q.bias is None:
+        return None
+    return _attn_images(attn), mimg
+
+
 class Mlp(nn.Module):
     """M:16-34.  Parameter container; fused as LN -> fc1 -> GELU -> fc2 -> +residual inside the block ops."""
 
@@ -289,6 +311,16 @@ class CrossTransformerBlock3D(nn.Module):
         s1, s2 = _block_scales(self, x.shape[0], x.device)
         a = self.cross_attn
         co = self.conv_offset
+        imgs = _fused_block_images(self, a, x.shape[1:4]) if x.is_cuda else None
+        if imgs is not None:
+            cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
+            cwk = co[0].weight.detach().permute(2, 3, 4, 0, 1).reshape(27, self.hidden_channels, 2 * self.dim).contiguous()
+            w3 = co[3].weight.reshape(3, self.hidden_channels)
+            return ops.FusedCrossBlockFn.apply(
+                x.contiguous(), xa.contiguous(), s1, s2, self.num_heads, _current(imgs[0]), _current(imgs[1]),
+                self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight, a.proj.bias,
+                cw, cwk, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
+                self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
         cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
         cwk = None
         if ops.N.get_gemm_mode() == 1:      # tcgen05 forward reads the weight as [tap][out][in]
@@ -329,6 +361,13 @@ class TransformerBlock3D(nn.Module):
     def forward(self, x):
         s1, s2 = _block_scales(self, x.shape[0], x.device)
         a = self.self_attn
+        imgs = _fused_block_images(self, a, x.shape[1:4]) if x.is_cuda else None
+        if imgs is not None:
+            return ops.FusedSelfBlockFn.apply(
+                x.contiguous(), s1, s2, self.num_heads, _current(imgs[0]), _current(imgs[1]),
+                self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight, a.proj.bias,
+                self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
+                self.mlp.fc2.bias)
         return ops.SelfBlockFn.apply(
             x.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
@@ -522,7 +561,13 @@ class MicFormer(nn.Module):
         """Everything up to (not including) cat -> norm2 -> reverse_patch_embedding; vol is (B, 2, D, H, W)."""
         self._predraw_drop_path(vol.shape[0], vol.device)
         # the optimizer changed the weights since the last forward: rebuild all fused-kernel weight images in one launch
-        fused.model_refresh([i for i in (m.fused_images() for m in self.modules() if isinstance(m, Mlp)) if i is not None])
+        imgs = [m.fused_images() for m in self.modules() if isinstance(m, Mlp)]
+        if fused.enabled() and vol.is_cuda:
+            for m in self.modules():
+                if isinstance(m, (CrossTransformerBlock3D, TransformerBlock3D)) and (m.dim, m.dim // m.num_heads) in fused.FUSED_ATTN \
+                        and tuple(m.window_size) == (2, 2, 2):
+                    imgs.append(_attn_images(m.cross_attn if isinstance(m, CrossTransformerBlock3D) else m.self_attn))
+        fused.model_refresh([i for i in imgs if i is not None])
         moving = self.patch_embed(vol, 0)
         fixed = self.patch_embed(vol, 1)
         feats_m, feats_f = [], []

@@ -547,6 +547,136 @@ class CrossBlockFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# fully fused blocks (2x2x2 windows, C = 48: the train config's stage 0): two tcgen05 kernels per direction
+# ----------------------------------------------------------------------------------------------------------
+_ATTN_P = ("n1w", "n1b", "qw", "qb", "kvw", "kvb", "pw", "pb")
+
+
+def _grad_bufs(ps, like):
+    gs = [_acc(p) if _acc(p) is not None else _zeros(tuple(p.shape), like) for p in ps]
+    return gs, [_gret(p, g) for p, g in zip(ps, gs)]
+
+
+class FusedSelfBlockFn(torch.autograd.Function):
+    """TransformerBlock3D.forward (reference M:473-524) as two fused kernels: attention half (LN1, q|kv, 8-token window
+    attention, proj, residual) and MLP half (LN2, fc1, GELU, fc2, residual).  Saves only x and x1; the backward kernels
+    recompute everything else on chip and accumulate all 14 parameter gradients.
+
+    args: x, s1, s2, heads, attention images, MLP images, then norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b}, norm2.{w,b},
+    fc1.{w,b}, fc2.{w,b}."""
+
+    @staticmethod
+    def forward(ctx, x, s1, s2, heads, aimg, mimg, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b):
+        N.check_cuda_f32(x, n1w, qw, kvw, pw, f1w, f2w)
+        B, D, H, W, C = x.shape
+        x1 = F_.attn_block_fwd(x, None, aimg, n1w, n1b, qb, kvb, pb, s1, heads, LN_EPS)
+        y = F_.mlp_block_fwd(x1, mimg, n2w, n2b, f1b, f2b, s2, D * H * W, LN_EPS)
+        ctx.save_for_backward(x, x1, *([s1] if s1 is not None else []), *([s2] if s2 is not None else []))
+        ctx.meta = (heads, s1 is not None, s2 is not None)
+        ctx.params = (n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b)
+        ctx.imgs = (aimg, mimg)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        heads, has1, has2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        x, x1 = sv[:2]
+        rest = sv[2:]
+        s1 = rest.pop(0) if has1 else None
+        s2 = rest.pop(0) if has2 else None
+        n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b = ctx.params
+        aimg, mimg = ctx.imgs
+        B, D, H, W, C = x.shape
+        dy = dy.contiguous()
+        with zero_arena(12 * C * C + 64 * C + 4096, x):
+            mg, mret = _grad_bufs((n2w, n2b, f1w, f1b, f2w, f2b), x)
+            dx1 = F_.mlp_block_bwd(dy, x1, mimg, n2w, n2b, f1b, s2, D * H * W, LN_EPS, *mg)
+            ag, aret = _grad_bufs((n1w, n1b, qw, qb, kvw, kvb, pw, pb), x)
+            dx, _ = F_.attn_block_bwd(dx1, x, None, aimg, n1w, n1b, qb, kvb, s1, heads, LN_EPS, *ag)
+        return (dx, None, None, None, None, None, *aret, *mret)
+
+
+class FusedCrossBlockFn(torch.autograd.Function):
+    """CrossTransformerBlock3D.forward (reference M:339-426) with the attention and MLP halves as fused kernels.  The
+    offset branch (LN(x) -> conv_offset on cat[LN(x), xa] -> offset head -> deformable resampling of xa) keeps its own
+    kernels and produces the k/v source ``samp`` of the fused attention kernel.
+
+    args: x, xa, s1, s2, heads, attention images, MLP images, then the parameters in CrossBlockFn's order."""
+
+    @staticmethod
+    def forward(ctx, x, xa, s1, s2, heads, aimg, mimg, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cwk, cb, lnw, lnb, w3, n2w,
+                n2b, f1w, f1b, f2w, f2b):
+        N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
+        B, D, H, W, C = x.shape
+        dims = (B, D, H, W)
+        P = B * D * H * W
+        HC = cw.shape[-1]
+        xn, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims)
+        h16 = _empty((P, HC), x)
+        conv3_fwd(xn, xa, cw, cwk, cb, h16, B, (D, H, W), HC, False)
+        pos = _empty((P, 3), x)
+        N.call("mic_offset_head_fwd", N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(pos), B, D, H, W, HC, LN_EPS)
+        samp = torch.empty_like(x)
+        N.call("mic_deform_sample_fwd", N.ptr(xa), N.ptr(pos), N.ptr(samp), B, D, H, W, D, H, W, C)
+        x1 = F_.attn_block_fwd(x, samp, aimg, n1w, n1b, qb, kvb, pb, s1, heads, LN_EPS)
+        y = F_.mlp_block_fwd(x1, mimg, n2w, n2b, f1b, f2b, s2, D * H * W, LN_EPS)
+        ctx.save_for_backward(x, xa, xn, mean1, rstd1, h16, pos, samp, x1, *([s1] if s1 is not None else []),
+                              *([s2] if s2 is not None else []))
+        ctx.meta = (heads, s1 is not None, s2 is not None)
+        ctx.params = (n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cb, lnw, lnb, w3, n2w, n2b, f1w, f1b, f2w, f2b)
+        ctx.imgs = (aimg, mimg)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        heads, has1, has2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        x, xa, xn, mean1, rstd1, h16, pos, samp, x1 = sv[:9]
+        rest = sv[9:]
+        s1 = rest.pop(0) if has1 else None
+        s2 = rest.pop(0) if has2 else None
+        n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cb, lnw, lnb, w3, n2w, n2b, f1w, f1b, f2w, f2b = ctx.params
+        aimg, mimg = ctx.imgs
+        B, D, H, W, C = x.shape
+        dims = (B, D, H, W)
+        P = B * D * H * W
+        HC = cw.shape[-1]
+        dy = dy.contiguous()
+        with zero_arena(12 * C * C + 27 * 2 * C * HC + 64 * C + 8192 + P * C, x), side_branch() as sb:
+            mg, mret = _grad_bufs((n2w, n2b, f1w, f1b, f2w, f2b), x)
+            dx1 = F_.mlp_block_bwd(dy, x1, mimg, n2w, n2b, f1b, s2, D * H * W, LN_EPS, *mg)
+            # attention half: dxq = dx1 + LN1'(dq Wq) (the q path of norm1), dsamp = [dk|dv] Wkv; norm1's gradients through the
+            # q path are accumulated here, those through the offset branch by ln_bwd below (LayerNorm' is linear in its input)
+            ag, aret = _grad_bufs((n1w, n1b, qw, qb, kvw, kvb, pw, pb), x)
+            dxq, dsamp = F_.attn_block_bwd(dx1, x, samp, aimg, n1w, n1b, qb, kvb, s1, heads, LN_EPS, *ag)
+            dxa = _zeros((B, D, H, W, C), x)
+            dpos = _empty((P, 3), x)
+            N.call("mic_deform_sample_bwd", N.ptr(dsamp), N.ptr(xa), N.ptr(pos), N.ptr(dxa), N.ptr(dpos), B, D, H, W, D, H, W, C)
+            dh16 = _empty((P, HC), x)
+            dlnw = _acc(lnw) if _acc(lnw) is not None else _zeros((HC,), x)
+            dlnb = _acc(lnb) if _acc(lnb) is not None else _zeros((HC,), x)
+            dw3 = _zeros((3, HC), x)
+            N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
+                   N.ptr(dlnb), N.ptr(dw3), B, D, H, W, HC, LN_EPS)
+            dcw = _zeros(tuple(cw.shape), x)
+            dcb = _acc(cb) if _acc(cb) is not None else _zeros((HC,), x)
+            sb.hold(dh16, xn, xa)
+            sb.run(conv3_bwd_weight, dh16, xn, xa, dcw, dcb, B, (D, H, W), HC, False)
+            dxn = _empty((B, D, H, W, C), x)
+            conv3_bwd_data(dh16, cw, dxn, False, dxa, True, B, (D, H, W), HC, False)
+            # second use of norm1's backward: the gradient that reached LN(x) through the offset conv
+            dx, _, dn1w2, dn1b2 = ln_bwd(dxn, x, None, n1w, mean1, rstd1, dxq, None, dims, beta=n1b)
+            if _acc(n1w) is None:                    # no arena: add the two contributions of norm1's parameters
+                aret[0] = aret[0] + dn1w2
+                aret[1] = aret[1] + dn1b2
+        return (dx, dxa, None, None, None, None, None, *aret, dcw, None, _gret(cb, dcb), _gret(lnw, dlnw), _gret(lnb, dlnb),
+                dw3, *mret)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # non-block operators
 # ----------------------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):

@@ -85,3 +85,143 @@ def test_fused_mlp_backward(C, T):
     fused.mlp_block_bwd(dy, x, img, p["gamma"], p["beta"], p["b1"], rs, rps, 1e-5, grads["gamma"], grads["beta"],
                         grads["w1"], grads["b1"], grads["w2"], grads["b2"])
     assert rel(grads["w1"], 2 * p64["w1"].grad) < 3e-5
+
+
+def _attn_case(C, dims, seed, dev, cross):
+    g = torch.Generator().manual_seed(seed)
+    B, D, H, W = dims
+    x = torch.randn(B, D, H, W, C, generator=g)
+    src = torch.randn(B, D, H, W, C, generator=g) if cross else None
+    u = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) * 0.3
+    p = dict(gamma=1.0 + 0.1 * torch.randn(C, generator=g), beta=0.1 * torch.randn(C, generator=g), wq=u(C, C),
+             bq=0.1 * torch.randn(C, generator=g), wkv=u(2 * C, C), bkv=0.1 * torch.randn(2 * C, generator=g), wp=u(C, C),
+             bp=0.1 * torch.randn(C, generator=g))
+    return x.to(dev), (src.to(dev) if cross else None), {k: v.to(dev) for k, v in p.items()}
+
+
+def _win(t):          # (B, D, H, W, C) -> (B*nW, 8, C), reference window_partition M:37-50 with window 2x2x2
+    B, D, H, W, C = t.shape
+    return t.view(B, D // 2, 2, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, 8, C)
+
+
+def _unwin(t, shape):
+    B, D, H, W, C = shape
+    return t.view(B, D // 2, H // 2, W // 2, 2, 2, 2, C).permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(B, D, H, W, C)
+
+
+def _attn_ref64(x, src, p, heads, rowscale=None):
+    x = x.double()
+    C = x.shape[-1]
+    xn = torch.nn.functional.layer_norm(x, (C,), p["gamma"].double(), p["beta"].double(), 1e-5)
+    kvin = xn if src is None else src.double()
+    q = _win(xn) @ p["wq"].double().t() + p["bq"].double()
+    kv = _win(kvin) @ p["wkv"].double().t() + p["bkv"].double()
+    nw = q.shape[0]
+    hd = C // heads
+    q = q.view(nw, 8, heads, hd).transpose(1, 2) * hd ** -0.5
+    k = kv[..., :C].reshape(nw, 8, heads, hd).transpose(1, 2)
+    v = kv[..., C:].reshape(nw, 8, heads, hd).transpose(1, 2)
+    o = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).transpose(1, 2).reshape(nw, 8, C)
+    o = _unwin(o @ p["wp"].double().t() + p["bp"].double(), x.shape)
+    if rowscale is not None:
+        o = o * rowscale.double().view(-1, 1, 1, 1, 1)
+    return x + o
+
+
+@pytest.mark.parametrize("heads,dims,cross", [(3, (1, 4, 4, 8), False), (3, (2, 6, 4, 10), True), (2, (1, 8, 8, 8), True),
+                                              (3, (2, 32, 32, 32), False)])
+def test_fused_attention_forward(heads, dims, cross):
+    from micformer_b200 import fused
+    dev = torch.device("cuda")
+    C = 48
+    x, src, p = _attn_case(C, dims, 31 + heads + dims[1], dev, cross)
+    img = fused.attn_images(p["wq"], p["wkv"], p["wp"])
+    img.refresh()
+    rs = torch.tensor([1.25, 0.0][: dims[0]], device=dev)
+    for rowscale in (None, rs):
+        y = fused.attn_block_fwd(x, src, img, p["gamma"], p["beta"], p["bq"], p["bkv"], p["bp"], rowscale, heads, 1e-5)
+        ref = _attn_ref64(x, src, p, heads, rowscale)
+        err = float((y.double() - ref).abs().max() / ref.abs().max())
+        assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("heads,dims,cross", [(3, (1, 4, 4, 8), False), (3, (2, 6, 4, 10), True), (2, (1, 8, 8, 8), True),
+                                              (2, (1, 4, 4, 4), False), (3, (2, 32, 32, 32), True)])
+def test_fused_attention_backward(heads, dims, cross):
+    from micformer_b200 import fused
+    dev = torch.device("cuda")
+    C = 48
+    x, src, p = _attn_case(C, dims, 77 + heads + dims[1], dev, cross)
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(*x.shape, generator=g).to(dev)
+    rs = torch.tensor([1.25, 0.5][: dims[0]], device=dev)
+    img = fused.attn_images(p["wq"], p["wkv"], p["wp"])
+    img.refresh()
+    names = ("gamma", "beta", "wq", "bq", "wkv", "bkv", "wp", "bp")
+    grads = {k: torch.zeros_like(p[k]) for k in names}
+    dx, dsrc = fused.attn_block_bwd(dy, x, src, img, p["gamma"], p["beta"], p["bq"], p["bkv"], rs, heads, 1e-5,
+                                    *[grads[k] for k in names])
+    x64 = x.double().requires_grad_(True)
+    s64 = src.double().requires_grad_(True) if cross else None
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    _attn_ref64(x64, s64, p64, heads, rs).backward(dy.double())
+    def rel(a, b):
+        return float((a.double() - b).norm() / (b.norm() + 1e-30))
+    assert rel(dx, x64.grad) < 2e-5, rel(dx, x64.grad)
+    if cross:
+        assert rel(dsrc, s64.grad) < 2e-5, rel(dsrc, s64.grad)
+    else:
+        assert dsrc is None
+    for k in names:
+        assert rel(grads[k], p64[k].grad) < 3e-5, (k, rel(grads[k], p64[k].grad))
+
+
+@pytest.mark.parametrize("cross,heads,dims,train", [(False, 3, (2, 4, 4, 8), False), (True, 3, (2, 4, 6, 8), False),
+                                                    (True, 2, (1, 8, 8, 8), True), (False, 3, (1, 16, 16, 16), True)])
+def test_fused_blocks_match_exact_path(cross, heads, dims, train):
+    """The nn.Module surface: a (Cross)TransformerBlock3D in tensor-core mode (fully fused kernels) vs the same module in
+    exact-fp32 mode (unfused CUDA-core kernels, the path pinned to the reference's golden vectors): output, input gradients
+    and every parameter gradient; train=True shares pre-drawn DropPath scales between the two runs."""
+    from micformer_b200 import _native as N, ops
+    from micformer_b200.models.MICFormer_self import CrossTransformerBlock3D, TransformerBlock3D
+    dev = torch.device("cuda")
+    C = 48
+    torch.manual_seed(3)
+    cls = CrossTransformerBlock3D if cross else TransformerBlock3D
+    blk = cls(dim=C, num_heads=heads, window_size=(2, 2, 2), qkv_bias=True, drop_path=0.3).to(dev)
+    with torch.no_grad():
+        for prm in blk.parameters():
+            prm.add_(0.05 * torch.randn_like(prm))
+    blk.train(train)
+    B = dims[0]
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, *dims[1:], C, generator=g).to(dev)
+    xa = torch.randn(B, *dims[1:], C, generator=g).to(dev)
+    gy = torch.randn(B, *dims[1:], C, generator=g).to(dev)
+    scales = (torch.tensor([1 / 0.7, 0.0][:B], device=dev), torch.tensor([0.0, 1 / 0.7][:B], device=dev)) if train else None
+
+    def run(mode):
+        N.set_gemm_mode(mode)
+        for prm in blk.parameters():
+            prm.grad = None
+        xi, xai = x.clone().requires_grad_(True), xa.clone().requires_grad_(True)
+        if scales is not None:
+            blk.__dict__["_dp_scales"] = scales
+        N.reset_launch_count()
+        y = blk(xi, xai) if cross else blk(xi)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        launches = N.launch_count()
+        gr = {k: prm.grad.clone() for k, prm in blk.named_parameters()}
+        return y.detach(), xi.grad, (xai.grad if cross else None), gr, launches
+
+    y0, dx0, dxa0, g0, l0 = run(0)
+    y1, dx1, dxa1, g1, l1 = run(1)
+    assert l1 < l0 and l1 <= (20 if cross else 6), (l0, l1)       # the fused path ran: 4 block kernels + 2 image refreshes (+ offset branch)
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    assert rel(y1, y0) < 5e-5 and rel(dx1, dx0) < 1e-4
+    if cross:
+        assert rel(dxa1, dxa0) < 2e-3          # through the TF32 tensor-core offset conv
+    for k in g0:
+        tol = 5e-3 if ("conv_offset" in k or (cross and "norm1" in k)) else 1e-4
+        assert rel(g1[k], g0[k]) < tol, (k, rel(g1[k], g0[k]))
