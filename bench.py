@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
     ap.add_argument("--no-attn-isolation", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the window-7 step and the eager-CUDA context block")
     ap.add_argument("--arena", type=int, default=int(os.environ.get("MICFORMER_GRAD_ARENA", "-1")),
                     help="1: gradients accumulate directly into one flat buffer (micformer_b200.arena.GradArena) and the "
                          "all-reduce runs in place on it; default: on for N > 1 (measured neutral at N = 1)")
@@ -56,6 +57,31 @@ def cfg_of(name):
 
 WORKLOADS = {"train": "MicFormer train config Head(embed_dim=48,num_classes=8,window=2^3,depths 2-2-6-2)",
              "w7": "MicFormer Head(embed_dim=96,num_classes=8,window=7^3,depths 2-2-6-2)"}
+DTYPE = ("f32 storage; tensor-core products: split-bf16 (hi+lo, 3 MMAs, ~2^-17) in the fused stage-0 blocks, 3xTF32 forward / "
+         "TF32 backward GEMMs and convs elsewhere; fp32 accumulate, fp32 LayerNorm / softmax / GELU / loss / Adam")
+
+
+def config_of(args):
+    """the ONE config dict both arms print (the driver compares them key by key)"""
+    return {"workload": WORKLOADS[args.config], "volumes_per_gpu_per_step": args.batch, "volume": f"2x(1,{args.size}^3)",
+            "step": "fwd + MDiceLoss + bwd + grad all-reduce (N>1) + Adam", "mode": "eval" if args.eval_mode else "train",
+            "l2": "per-step working set (activations + 247 MB weights/grads) >> 126 MB L2; no explicit flush"}
+
+
+def family(kernel_key: str) -> str:
+    """kernel-table key (C-ABI name + [shape]) -> kernel family, the granularity the roofline is reported at"""
+    n = kernel_key.split("[")[0]
+    if n.startswith("mic_linear_"):
+        return "gemm (mic_linear_fwd/bwd_data/bwd_weight: tcgen05 TF32 GEMMs of the unfused stages 1-3, patch ops, tail)"
+    if n.startswith("mic_conv3"):
+        return "conv3 (3x3x3 convs: offset nets, out_conv)"
+    if n.startswith("mic_mlp_block") or n.startswith("mic_attn_block"):
+        return "fused_block (mic_attn_block_* / mic_mlp_block_*: fused tcgen05 half-blocks of stage 0)"
+    if n.startswith("mic_layernorm"):
+        return "layernorm"
+    if n.startswith("mic_window_attn"):
+        return "window_attn (unfused small-window attention, stages 1-3)"
+    return n
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -122,7 +148,7 @@ def oracle_step_fn(cfg, B, S, train_mode, threads):
         loss = O.mdice_loss(logits, lab)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -144,9 +170,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "volumes/sec (2-modal 128^3) fwd+bwd", "value": val, "unit": "volumes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "volumes_per_step": B, "volume": f"2x(1,{args.size}^3)",
-                   "mode": "eval" if args.eval_mode else "train"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch CPU ops)", "data": "synthetic",
+        "config": config_of(args),
         "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps of batch {B} at {args.size}^3, fwd+MDiceLoss+bwd+Adam, "
                                    f"oracle port of the reference's torch-CPU path, {threads} threads"},
@@ -154,6 +179,86 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- secondary blocks
+def secondary_w7(dev, args, steps=10):
+    """Head(embed_dim=96, window 7^3) -- the model family BASELINE config 4's attention shape comes from -- same step
+    (fwd + MDiceLoss + bwd + fused Adam, batch 2 of 2x(1,128^3)), eager launches, CUDA events, `steps` timed steps."""
+    from micformer_b200.models.MICFormer_self import Head
+    from micformer_b200.loss.dice import MDiceLoss
+    from micformer_b200.optim import FusedAdam
+    from oracle import micformer_oracle as O
+    cfg = O.W7
+    torch.manual_seed(0)
+    model = Head(embed_dim=cfg.embed_dim, num_classes=cfg.num_classes, window_size=cfg.window_size).to(dev)
+    model.train(not args.eval_mode)
+    crit = MDiceLoss()
+    opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)
+    x, lab = O.synth_inputs(args.batch, args.size, cfg.num_classes, seed=1)
+    x, lab = x.to(dev), lab.to(dev)
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), lab)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": WORKLOADS["w7"], "volumes_per_step": args.batch, "steps": steps, "warmup": 3, "ms_per_step": round(ms, 3),
+            "volumes_per_s": round(args.batch / ms * 1e3, 2), "loss": round(float(loss.detach()), 6),
+            "note": "eager launches (no CUDA graph); attention forward on tcgen05, backward on CUDA cores"}
+
+
+def eager_cuda(dev, cfg, B, S, train_mode, steps=3):
+    """The reference's own ops (the oracle port: F.linear / bmm / softmax / conv3d / layer_norm / grid_sample ...) executed
+    EAGERLY on this GPU by torch -- what the unmodified reference would run on a B200 -- with the script's settings
+    (cudnn off, fp32 matmuls: train_mmwhs_noPad.py:28-29) and with cuDNN + TF32 enabled.  Informational context only."""
+    from oracle import micformer_oracle as O
+    out = {}
+    x, lab = O.synth_inputs(B, S, cfg.num_classes, seed=1)
+    x, lab = x.to(dev), lab.to(dev)
+    for name, cudnn_on, tf32 in (("script_settings_cudnn_off_fp32", False, False), ("cudnn_tf32", True, True)):
+        try:
+            torch.backends.cudnn.enabled = cudnn_on
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            params = {k: torch.nn.Parameter(v.to(dev)) for k, v in O.synth_state_dict(cfg, seed=0).items()}
+            opt = torch.optim.Adam(params.values(), lr=1e-4, weight_decay=0.0)
+            gen = torch.Generator().manual_seed(0)
+
+            def one():
+                opt.zero_grad(set_to_none=True)
+                loss = O.mdice_loss(O.head_forward(x, params, cfg, training=train_mode, gen=gen), lab)
+                loss.backward()
+                opt.step()
+
+            one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": round(ms, 2), "volumes_per_s": round(B / ms * 1e3, 2), "steps": steps}
+            del params, opt
+            torch.cuda.empty_cache()
+        except Exception as e:      # informational block: never fail the bench line
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    torch.backends.cudnn.enabled = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["note"] = ("oracle port of the reference ops, eager torch on the same GPU, same batch and step; not the product path")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -308,13 +413,13 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_val = world * B * args.steps / (ms_e2e / 1e3)
 
-    # --- per-kernel pass (CUDA events around every C-ABI launch, same steps) -> roofline of the dominant kernel
-    roofline, shares = None, None
+    # --- per-kernel pass (CUDA events around every C-ABI launch, same steps) -> roofline of the dominant kernel FAMILY
+    roofline, shares, step_roofline = None, None, None
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk)); peaks["src"] = "measured"
     if rank == 0 and world == 1 and not args.no_kernel_pass:      # N = 1 only: the pass steps the model on this rank alone
-        peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk)); peaks["src"] = "measured"
         _native.profile_begin()
         ksteps = min(args.steps, 3)
         for _ in range(ksteps):
@@ -322,10 +427,16 @@ def run_ours(args):
         prof = _native.profile_end()
         tot = sum(v["ms"] for v in prof.values())
         top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
-        shares = [{"kernel": k, "share": round(v["ms"] / tot, 4), "ms_per_step": round(v["ms"] / ksteps, 4),
+        fam = {}
+        for k, v in prof.items():
+            f = fam.setdefault(family(k), {"ms": 0.0, "calls": 0, "bytes": 0, "flops": 0})
+            for key in f:
+                f[key] += v[key]
+        ftop = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
+        shares = [{"family": k, "share": round(v["ms"] / tot, 4), "ms_per_step": round(v["ms"] / ksteps, 4),
                    "calls_per_step": v["calls"] // ksteps,
                    "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] > 0 else None,
-                   "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["ms"] > 0 else None} for k, v in top[:12]]
+                   "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["ms"] > 0 else None} for k, v in ftop[:8]]
         if args.dump_kernels:
             os.makedirs(os.path.dirname(os.path.abspath(args.dump_kernels)), exist_ok=True)
             with open(args.dump_kernels, "w") as f:
@@ -335,14 +446,36 @@ def run_ours(args):
                                         "gbs": v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else None,
                                         "tflops": v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else None}
                                        for k, v in top]}, f, indent=1)
-        name, v = top[0]
-        ach = v["bytes"] / (v["ms"] * 1e6)        # GB/s: algorithmic bytes / event-timed duration
+        name, v = ftop[0]
+        ach = v["bytes"] / (v["ms"] * 1e6)        # GB/s: algorithmic bytes / event-timed duration, summed over the family
+        # measured DRAM traffic of the same family from the committed ncu pass over one step (profiles/r02_traffic.json:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, made by scripts/traffic_pass.sh)
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tj):
+            ent = json.load(open(tj)).get("families", {}).get(name.split(" ")[0])
+            if ent:
+                traffic = ent.get("dram_bytes_per_launch")
         roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
                     "peak_source": peaks["src"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
-                    "traffic": None, "avg_launch_ms": round(v["ms"] / v["calls"], 5),
+                    "traffic": traffic, "launches_per_step": v["calls"] // ksteps,
+                    "avg_launch_ms": round(v["ms"] / v["calls"], 5),
                     "algorithmic_bytes_per_launch": v["bytes"] // v["calls"],
                     "algorithmic_tflops": round(v["flops"] / (v["ms"] * 1e9), 2),
-                    "share_of_kernel_time": round(v["ms"] / tot, 4)}
+                    "share_of_kernel_time": round(v["ms"] / tot, 4),
+                    "note": "family = all launches of these entry points in one step; achieved = summed algorithmic bytes / summed "
+                            "CUDA-event time (per-launch, serialised)"}
+        # whole step: algorithmic work of every kernel of one step against the step time of the timed region
+        gflop = sum(v["flops"] for v in prof.values()) / ksteps / 1e9
+        gbyte = sum(v["bytes"] for v in prof.values()) / ksteps / 1e9
+        step_ms = ms / args.steps
+        step_roofline = {"gflop_per_step": round(gflop, 1), "algorithmic_gb_per_step": round(gbyte, 2),
+                         "tflops": round(gflop / step_ms, 2), "gbs": round(gbyte / step_ms * 1e3, 1),
+                         "frac_of_hbm_peak": round(gbyte / step_ms * 1e3 / peaks["hbm_gbs"], 4),
+                         "frac_of_tf32_peak": round(gflop / step_ms / (peaks.get("bf16_tflops", 1590.0) / 2.0), 4),
+                         "serialised_kernel_ms_per_step": round(tot / ksteps, 3),
+                         "note": "sum of per-kernel algorithmic bytes / flops (micformer_b200/_native.COST) over one step / "
+                                 "graph-replayed step time; tf32 peak = half the measured bf16 burst"}
     # --- BASELINE.json's second metric: the cross-modal attention kernel in isolation (config 4: 4096 windows of 343
     #     tokens, 96 channels, 3 heads of 32; fp32 I/O, TF32 tensor cores), timed alone with CUDA events
     attn = None
@@ -362,16 +495,32 @@ def run_ours(args):
         ams = a0.elapsed_time(a1) / 5
         aflops = 4.0 * Bw * Ha * 343 * 343 * 32
         abytes = 4.0 * (4 * Bw * 343 * Ca + Bw * 343 * Ha)
-        pk = peaks if roofline is not None else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+        pk = peaks
         tf32_peak = pk.get("bf16_tflops", 1590.0) / 2.0          # dense TF32 = half the measured bf16 cuBLAS burst figure
         attn = {"workload": "cross-modal window attention forward, 4096 windows x 343 tokens x 96 ch x 3 heads (config 4), fp32 I/O",
                 "ms": round(ams, 4), "tflops": round(aflops / ams / 1e9, 1), "tf32_peak_tflops": round(tf32_peak, 1),
-                "frac_of_tf32_peak": round(aflops / ams / 1e9 / tf32_peak, 4), "algorithmic_gbs": round(abytes / ams / 1e6, 1),
+                "frac_of_tf32_peak": round(aflops / ams / 1e9 / tf32_peak, 4),
+                "frac_of_bf16_peak": round(aflops / ams / 1e9 / pk.get("bf16_tflops", 1590.0), 4),
+                "algorithmic_gbs": round(abytes / ams / 1e6, 1),
                 "frac_of_hbm_peak": round(abytes / ams / 1e6 / pk["hbm_gbs"], 4),
                 "note": "fp32 Q/K/V/O make this shape HBM-bound below the tensor ridge: 2.16 GB / measured copy bandwidth = 0.33 ms floor"}
         del qkv
     if world > 1:
         dist.barrier()
+
+    # --- secondary configs (N = 1): the window-7 model (the shape family of BASELINE config 4) through the same step, and the
+    #     reference ops eager on this GPU -- the only GPU-vs-GPU context this project has: informational
+    secondary, eager = None, None
+    run_info = {"parallelism": f"dp{world}", "gemm_mode": args.gemm_mode, "cuda_graph": bool(args.graph),
+                "fused_blocks": os.environ.get("MICFORMER_FUSED", "1") != "0", "grad_arena": arena is not None}
+    if rank == 0 and world == 1 and not args.no_secondary and args.config == "train":
+        del graph
+        model = opt = arena = sync = None
+        torch.cuda.empty_cache()
+        secondary = {"w7_step": secondary_w7(dev, args), }
+        torch.cuda.empty_cache()
+        eager = eager_cuda(dev, cfg, B, S, not args.eval_mode)
+        torch.cuda.empty_cache()
 
     # --- CPU baseline on the host cores (rank 0, N=1 only): oracle port, bounded sample -------------------
     cpu = None
@@ -391,17 +540,15 @@ def run_ours(args):
         line = {
             "metric": "volumes/sec (2-modal 128^3) fwd+bwd", "value": value, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "volumes_per_gpu_per_step": B, "volume": f"2x(1,{S}^3)",
-                       "step": "fwd + MDiceLoss + bwd + grad all-reduce (N>1) + fused Adam", "parallelism": f"dp{world}",
-                       "mode": "eval" if args.eval_mode else "train", "gemm_mode": args.gemm_mode,
-                       "cuda_graph": bool(args.graph),
-                       "l2": "per-step working set (activations + 247 MB weights/grads) >> 126 MB L2; no explicit flush"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": config_of(args),
+            "run": run_info,
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "attention_kernel": attn, "kernel_shares": shares,
+            "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "attention_kernel": attn,
+            "kernel_shares": shares, "secondary": secondary, "eager_cuda": eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

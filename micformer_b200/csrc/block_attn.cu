@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(AttnCfg<C, HD>::THREADS, 1) attn_block_fwd_ker
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++n) {
             const int64_t grow = wg.row_of((int64_t)t * 16 + (row >> 3), row & 7, a.nwin_total);
             const bool ok = grow >= 0;
+            if (hh == 0 || (hh == 1 && cross)) {          // the next tile's rows start their way to L2 now
+                const int64_t gnext = t + (int)gridDim.x < a.ntiles ? wg.row_of((int64_t)(t + gridDim.x) * 16 + (row >> 3), row & 7, a.nwin_total) : -1;
+                if (gnext >= 0) prefetch_l2((hh == 0 ? a.x : a.kvsrc) + gnext * C, C * 4);
+            }
             // ---- operand tiles: head-0 warps LayerNorm x, head-1 warps stage the k/v source of a cross block
             if (hh == 0 || (hh == 1 && cross)) {
                 float r[C];

@@ -30,9 +30,9 @@ struct AttnBwdCfg {
     static constexpr int PAR = W_P + 2 * WC;                 // gamma[C] beta[C] bq[C] bkv[2C]
     static constexpr int BAR = PAR + 4 * 5 * C;
     static constexpr int SMEM = BAR + 256 + 1024;
-    static constexpr int T_Q = 0, T_K = CP, T_V = CP + C, T_DO = CP + 2 * C, T_DWP = 192, T_DWQ = 192 + CP, T_DWKV = 192 + 2 * CP;
-    static constexpr int NG = (3 * HD + 31) / 32;            // 32-column groups of [dq_h | dk_h | dv_h] for the bias gradients
-    static_assert(T_DO + CP <= 192 && T_DWKV + CP <= 512, "TMEM budget");
+    static constexpr int NB = CP + 16;                       // weight-gradient tiles carry one extra "ones" column: the bias gradient
+    static constexpr int T_Q = 0, T_K = CP, T_V = CP + C, T_DO = CP + 2 * C, T_DWP = 192, T_DWQ = 192 + NB, T_DWKV = 192 + 2 * NB;
+    static_assert(T_DO + CP <= 192 && T_DWKV + NB <= 512 && NB <= 64, "TMEM budget / ones column inside the 64-feature panel");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(W_A % 1024 == 0 && W_P % 1024 == 0 && WC % 1024 == 0, "swizzle alignment");
 };
@@ -56,7 +56,7 @@ __device__ __forceinline__ void transpose8(float (&v)[8], int l) {
 template <int C, int HD>
 __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_kernel(const AttnBwdArgs a) {
     using K = AttnBwdCfg<C, HD>;
-    constexpr int CP = K::CP, HEADS = K::HEADS, TILE = K::TILE, WC = K::WC, WKV = K::WKV, NG = K::NG;
+    constexpr int CP = K::CP, HEADS = K::HEADS, TILE = K::TILE, WC = K::WC, WKV = K::WKV, NB = K::NB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sXN = smem + K::R_XN;    // hi, lo (+TILE)
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
 
     constexpr uint32_t id_c = idesc_bf16(128, CP, false, false);
     constexpr uint32_t id_kv = idesc_bf16(128, 2 * C, false, false);
-    constexpr uint32_t id_dw = idesc_bf16(128, CP, true, true);
+    constexpr uint32_t id_dw = idesc_bf16(128, NB, true, true);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -202,16 +202,21 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
         }
         asm volatile("bar.sync 1, %0;" ::"n"(K::ROW_WARPS * 32) : "memory");
         WinGeom wg(a.D, a.H, a.W);
-        float bacc[NG];                           // bias-gradient partial sums: lane l of group g <-> [dq_h|dk_h|dv_h][32 g + l]
-#pragma unroll
-        for (int g = 0; g < NG; ++g) bacc[g] = 0.f;
-        float cacc0[2] = {0.f, 0.f}, cacc1[2] = {0.f, 0.f};      // STG_X warps: dgamma, dbeta;  STG_DY warps: dbp
+        float cacc0[2] = {0.f, 0.f}, cacc1[2] = {0.f, 0.f};      // STG_X warps: dgamma, dbeta partial sums
         uint32_t n = 0;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++n) {
             const int64_t grow = wg.row_of((int64_t)t * 16 + (row >> 3), row & 7, a.nwin_total);
             const bool ok = grow >= 0;
             float mean = 0.f, rstd = 0.f;
-            // ---- stage the operand tiles
+            {   // the next tile's rows start their way to L2 now
+                const int64_t gnext = t + (int)gridDim.x < a.ntiles ? wg.row_of((int64_t)(t + gridDim.x) * 16 + (row >> 3), row & 7, a.nwin_total) : -1;
+                if (gnext >= 0) {
+                    if (hh == STG_X) prefetch_l2(a.x + gnext * C, C * 4);
+                    if (hh == STG_DY) prefetch_l2(a.dy + gnext * C, C * 4);
+                    if (hh == STG_SP && cross) prefetch_l2(a.kvsrc + gnext * C, C * 4);
+                }
+            }
+            // ---- stage the operand tiles (xn and the k/v source carry the ones column of the bias gradients)
             if (hh == STG_X) {
                 float r[C];
                 load_row<C>(a.x, grow, ok, r);
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
 #pragma unroll
                 for (int i = 0; i < C; ++i) r[i] = ok ? (r[i] - mean) * rstd * sg[i] + sbt[i] : 0.f;
                 store_row_tile<C>(sXN, sXN + TILE, row, r);
+                store_ones_chunk(sXN, sXN + TILE, row, CP / 8);
             }
             if (hh == STG_DY) {
                 float r[C];
@@ -227,18 +233,12 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
 #pragma unroll
                 for (int i = 0; i < C; ++i) r[i] *= rs;
                 store_row_tile<C>(sDX, sDX + TILE, row, r);
-#pragma unroll
-                for (int gq = 0; gq < (C + 31) / 32; ++gq) {
-                    float v[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = (gq * 32 + e) < C ? r[(gq * 32 + e) < C ? gq * 32 + e : 0] : 0.f;
-                    cacc0[gq] += warp_colsum32(v, lane);
-                }
             }
             if (hh == STG_SP && cross) {
                 float r[C];
                 load_row<C>(a.kvsrc, grow, ok, r);
                 store_row_tile<C>(sSP, sSP + TILE, row, r);
+                store_ones_chunk(sSP, sSP + TILE, row, CP / 8);
             }
             fence_async_smem();
             __syncwarp();
@@ -300,10 +300,11 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
                 }
 #pragma unroll
                 for (int c = 0; c < HD / 8; ++c) store_chunk(sO, sO + TILE, row, (hh * HD) / 8 + c, o + 8 * c);
-                if (hh == 0 && CP > C) {
+                if (hh == 0) {
                     float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int c = C / 8; c < CP / 8; ++c) store_chunk(sO, sO + TILE, row, c, z);
+                    store_ones_chunk(sO, sO + TILE, row, CP / 8);          // dbp = column sums of rs*dy
                 }
             }
             fence_async_smem();
@@ -345,19 +346,6 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(dqkv_full);
-            // bias gradients: column sums of [dq_h | dk_h | dv_h] over the 32 rows of this warp
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                float v[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int idx = g * 32 + e;
-                    v[e] = idx < HD ? dq[idx < HD ? idx : 0]
-                                    : (idx < 2 * HD ? dk[(idx >= HD && idx < 2 * HD) ? idx - HD : 0]
-                                                    : (idx < 3 * HD ? dv[(idx >= 2 * HD && idx < 3 * HD) ? idx - 2 * HD : 0] : 0.f));
-                }
-                bacc[g] += warp_colsum32(v, lane);
-            }
             // ---- tile end: dxn (and dsrc) complete
             bar_wait(g2, n & 1);
             fence_after();
@@ -414,42 +402,32 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
         }
         // ---------------- flush
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int idx = g * 32 + lane;
-            if (idx < HD) atomicAdd(a.dbq + hh * HD + idx, bacc[g]);
-            else if (idx < 2 * HD) atomicAdd(a.dbkv + hh * HD + idx - HD, bacc[g]);
-            else if (idx < 3 * HD) atomicAdd(a.dbkv + C + hh * HD + idx - 2 * HD, bacc[g]);
-        }
-#pragma unroll
         for (int gq = 0; gq < (C + 31) / 32; ++gq) {
             const int col = gq * 32 + lane;
-            if (col < C) {
-                if (hh == STG_X) { atomicAdd(a.dgamma + col, cacc0[gq]); atomicAdd(a.dbeta + col, cacc1[gq]); }
-                if (hh == STG_DY) atomicAdd(a.dbp + col, cacc0[gq]);
-            }
+            if (col < C && hh == STG_X) { atomicAdd(a.dgamma + col, cacc0[gq]); atomicAdd(a.dbeta + col, cacc1[gq]); }
         }
         {
-            // weight-gradient accumulators: rows = output feature (TMEM lane), CP columns = input feature
-            float v[CP];
-            const uint32_t col = hh == 0 ? K::T_DWP : (hh == 1 ? K::T_DWQ : K::T_DWKV);
-            const int nrows = (hh == HEADS - 1 || hh >= 2) ? 2 * C : C;
-            float* dst = hh == 0 ? a.dWp : (hh == 1 ? a.dWq : a.dWkv);
-            auto flush = [&](uint32_t tcol, float* d, int rows) {
+            // weight-gradient accumulators: rows = output feature (TMEM lane), columns 0..C-1 = input feature, column CP = the
+            // product with the ones column = the bias gradient
+            float v[NB];
+            auto flush = [&](uint32_t tcol, float* d, float* db, int rows) {
 #pragma unroll
-                for (int c0 = 0; c0 < CP; c0 += 16) ld16(tmem + lane_base + tcol + c0, v + c0);
+                for (int c0 = 0; c0 < NB; c0 += 16) ld16(tmem + lane_base + tcol + c0, v + c0);
                 ld_wait();
                 if (row < rows) {
 #pragma unroll
                     for (int i = 0; i < C; ++i) atomicAdd(d + (int64_t)row * C + i, v[i]);
+                    atomicAdd(db + row, v[CP]);
                 }
             };
             if (HEADS >= 3) {
-                flush(col, dst, hh == 2 ? 2 * C : C);
+                if (hh == 0) flush(K::T_DWP, a.dWp, a.dbp, C);
+                else if (hh == 1) flush(K::T_DWQ, a.dWq, a.dbq, C);
+                else flush(K::T_DWKV, a.dWkv, a.dbkv, 2 * C);
             } else {                                   // two heads: head-0 warps flush dWp and dWkv
-                if (hh == 0) { flush(K::T_DWP, a.dWp, C); flush(K::T_DWKV, a.dWkv, 2 * C); }
-                else flush(K::T_DWQ, a.dWq, C);
+                if (hh == 0) { flush(K::T_DWP, a.dWp, a.dbp, C); flush(K::T_DWKV, a.dWkv, a.dbkv, 2 * C); }
+                else flush(K::T_DWQ, a.dWq, a.dbq, C);
             }
-            (void)nrows;
         }
     }
     fence_before();

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_block_fwd_kernel(const Mlp
             const uint32_t ph = n & 1;
             const int64_t grow = (int64_t)t * 128 + row;
             const bool ok = grow < a.T;
+            if (half == 0 && grow + (int64_t)gridDim.x * 128 < a.T) prefetch_l2(a.x + (grow + (int64_t)gridDim.x * 128) * C, C * 4);
             // ---- LayerNorm of the row -> split-bf16 A tile (each of the two threads of a row writes half of the chunks)
             float xr[C];
             if (ok) {

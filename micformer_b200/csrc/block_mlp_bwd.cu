@@ -48,9 +48,10 @@ struct MlpBwdCfg {
     static constexpr int OFF_PAR = OFF_RING + 2 * SLOT;      // b1[NCH*64] gamma[C] beta[C]
     static constexpr int OFF_BAR = OFF_PAR + 4 * (NCH * 64 + 2 * C);
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
-    static constexpr int T_HP = 0, T_DH = 64, T_DXN = 128, T_DW1 = 192, T_DW2 = 192 + NCH * CP;
+    static constexpr int NB = CP + 16;                       // dW1 tiles carry the "ones" column of xn: column CP = db1
+    static constexpr int T_HP = 0, T_DH = 64, T_DXN = 128, T_DW1 = 128 + CP, T_DW2 = T_DW1 + NCH * NB;
     static constexpr int TCOLS = 512;
-    static_assert(T_DW2 + NCH * CP <= 512, "TMEM budget");
+    static_assert(T_DW2 + NCH * CP <= 512 && NB <= 64, "TMEM budget / ones column inside the 64-feature panel");
     static_assert(C % 8 == 0 && C <= 64, "fused MLP backward: C multiple of 8, at most 64");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
@@ -58,7 +59,7 @@ struct MlpBwdCfg {
 template <int C>
 __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpBwdArgs a) {
     using K = MlpBwdCfg<C>;
-    constexpr int HID = K::HID, CP = K::CP, NCH = K::NCH, TILE = K::TILE;
+    constexpr int HID = K::HID, CP = K::CP, NCH = K::NCH, TILE = K::TILE, NB = K::NB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sXNh = smem + K::OFF_XN;  uint8_t* sXNl = sXNh + TILE;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
     constexpr uint32_t id_g1 = idesc_bf16(128, 64, false, false);
     constexpr uint32_t id_dx = idesc_bf16(128, CP, false, false);
     constexpr uint32_t id_dw = idesc_bf16(128, CP, true, true);
+    constexpr uint32_t id_dw1 = idesc_bf16(128, NB, true, true);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
                     fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma3(tmem + K::T_DW1 + c * CP, desc_mn(s32(sDHh) + ks * 2048, TILE), desc_mn(s32(sDHl) + ks * 2048, TILE),
-                             desc_mn(s32(sXNh) + ks * 2048, TILE), desc_mn(s32(sXNl) + ks * 2048, TILE), id_dw, (n | ks) ? 1u : 0u);
+                        mma3(tmem + K::T_DW1 + c * NB, desc_mn(s32(sDHh) + ks * 2048, TILE), desc_mn(s32(sDHl) + ks * 2048, TILE),
+                             desc_mn(s32(sXNh) + ks * 2048, TILE), desc_mn(s32(sXNl) + ks * 2048, TILE), id_dw1, (n | ks) ? 1u : 0u);
                     commit(g2_done);
                 }
             }
@@ -201,9 +203,6 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
             sb1[i] = v;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        float db1acc[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) db1acc[c] = 0.f;
         float cacc0[2] = {0.f, 0.f}, cacc1[2] = {0.f, 0.f};     // half 0: dgamma, dbeta;  half 1: db2, (unused)
         constexpr int NCHK = CP / 8;
         uint32_t g = 0, n = 0;
@@ -214,6 +213,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
             {
                 float r[C];
                 const float* src = half == 0 ? a.x : a.dy;
+                if (grow + (int64_t)gridDim.x * 128 < a.T) prefetch_l2(src + (grow + (int64_t)gridDim.x * 128) * C, C * 4);
                 if (ok) {
                     const float4* p = reinterpret_cast<const float4*>(src + grow * C);
 #pragma unroll
@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
                     for (int e = 0; e < 8; ++e) v8[e] = (c * 8 + e) < C ? r[(c * 8 + e) < C ? c * 8 + e : 0] : 0.f;
                     store_chunk(th, tl, row, c, v8);
                 }
+                if (half == 0) store_ones_chunk(sXNh, sXNl, row, NCHK);       // db1 = dh^T 1 comes out of the dW1 product
                 if (half == 1) {
 #pragma unroll
                     for (int gq = 0; gq < (C + 31) / 32; ++gq) {
@@ -292,10 +293,6 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) bar_arrive(hd_full);
-                const float cs = warp_colsum32(dv, lane);
-#pragma unroll
-                for (int cc = 0; cc < NCH; ++cc)                    // (static indexing keeps the accumulators in registers)
-                    if (cc == c) db1acc[cc] += cs;
             }
             // ---- tile end: dxn complete -> LayerNorm backward, dx = dy + LN'(dxn); dgamma / dbeta partial sums
             bar_wait(g2_done, (g - 1) & 1);
@@ -353,11 +350,6 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
         }
         // ---------------- flush: bias / LayerNorm gradients from registers, weight gradients from TMEM
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = c * 64 + half * 32 + lane;
-            if (col < HID) atomicAdd(a.db1 + col, db1acc[c]);
-        }
-#pragma unroll
         for (int gq = 0; gq < (C + 31) / 32; ++gq) {
             const int col = gq * 32 + lane;
             if (col < C) {
@@ -368,16 +360,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
         if (q < 2) {                      // accumulator rows 0..63 = hidden index inside the chunk (rows 64..127 are not used)
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-                float v[CP];
-                const uint32_t col = (half == 0 ? K::T_DW1 : K::T_DW2) + c * CP;
+                float v[NB];
+                const uint32_t col = half == 0 ? K::T_DW1 + c * NB : K::T_DW2 + c * CP;
 #pragma unroll
-                for (int c0 = 0; c0 < CP; c0 += 16) ld16(tmem + lane_base + col + c0, v + c0);
+                for (int c0 = 0; c0 < (half == 0 ? NB : CP); c0 += 16) ld16(tmem + lane_base + col + c0, v + c0);
                 ld_wait();
                 const int hid = c * 64 + row;
                 if (hid < HID) {
                     if (half == 0) {
 #pragma unroll
                         for (int i = 0; i < C; ++i) atomicAdd(a.dW1 + (int64_t)hid * C + i, v[i]);
+                        atomicAdd(a.db1 + hid, v[CP]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < C; ++i) atomicAdd(a.dW2 + (int64_t)i * HID + hid, v[i]);

@@ -159,6 +159,21 @@ __device__ __forceinline__ void store_chunk(uint8_t* hi_panel, uint8_t* lo_panel
     *reinterpret_cast<uint4*>(lo_panel + off) = l;
 }
 
+// pull a row of `bytes` bytes towards L2 (the next tile's rows, one tile ahead of their use)
+__device__ __forceinline__ void prefetch_l2(const void* p, int bytes) {
+    const char* c = reinterpret_cast<const char*>(p);
+    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 4));
+}
+// a "ones" feature column: chunk c of row r holds {1, 0, 0, 0, 0, 0, 0, 0} (hi) / zeros (lo).  With the column inside the
+// N range of a token-reduction product D = A^T B (B = this tile), column 8c of D is the column sum of A: the bias gradient
+// of a linear layer comes out of the weight-gradient MMA for free.
+__device__ __forceinline__ void store_ones_chunk(uint8_t* hi_panel, uint8_t* lo_panel, int r, int c) {
+    const uint32_t off = chunk_off(r, c);
+    *reinterpret_cast<uint4*>(hi_panel + off) = make_uint4(0x00003F80u, 0u, 0u, 0u);      // bf16(1.0) = 0x3F80 in the low half
+    *reinterpret_cast<uint4*>(lo_panel + off) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---------------------------------------------------------------------------------------------- GELU (erf form)
 // nn.GELU(approximate='none') and its derivative from ONE exponential: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
 // below the fp32 accumulation noise of the surrounding GEMMs), evaluated without cancellation on the negative side:

@@ -547,8 +547,8 @@ class MicFormer(nn.Module):
         torch kernels (one rand, one compare, one divide) instead of two tiny kernels per branch."""
         blocks = [b for b in self.modules() if isinstance(b, (CrossTransformerBlock3D, TransformerBlock3D))
                   and isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0.0]
-        if not blocks or not self.training:
-            return
+        if not blocks or not self.training or self.__dict__.get("_dp_external", False):
+            return          # (_dp_external: a caller supplies every block's `_dp_scales` itself -- shared-mask parity runs)
         keep = getattr(self, "_dp_keep", None)
         if keep is None or keep.device != device or keep.numel() != len(blocks):
             keep = torch.tensor([1.0 - b.drop_path.drop_prob for b in blocks], device=device).view(-1, 1, 1)

@@ -254,7 +254,7 @@ def stn_sample(src: Tensor, pos: Tensor) -> Tensor:
     align_corners=False."""
     shape = pos.shape[2:]
     grids = torch.meshgrid([torch.arange(0, s) for s in shape], indexing="ij")
-    grid = torch.stack(grids).unsqueeze(0).to(pos.dtype)
+    grid = torch.stack(grids).unsqueeze(0).to(device=pos.device, dtype=pos.dtype)
     new_locs = grid + pos
     comps = [2 * (new_locs[:, i] / (shape[i] - 1) - 0.5) for i in range(3)]
     g = torch.stack([comps[2], comps[1], comps[0]], dim=-1)
@@ -298,8 +298,8 @@ def _drop_path(x: Tensor, rate: float, training: bool, gen: Optional[torch.Gener
         return x
     keep = 1.0 - rate
     shape = (x.shape[0],) + (1,) * (x.ndim - 1)
-    mask = torch.empty(shape, dtype=x.dtype).bernoulli_(keep, generator=gen)
-    return x * mask.div_(keep)
+    mask = torch.empty(shape, dtype=x.dtype).bernoulli_(keep, generator=gen)     # drawn on the host (CPU generator)
+    return x * mask.div_(keep).to(x.device)
 
 
 def self_block(x: Tensor, p, pre: str, heads: int, window, dp=0.0, training=False, gen=None) -> Tensor:

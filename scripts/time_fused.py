@@ -44,3 +44,21 @@ if hasattr(fused, "mlp_block_bwd"):
     gw = [torch.zeros_like(t) for t in (n2w, n2b, f1w, f1b, f2w, f2b)]
     t_fb = timeit(lambda: fused.mlp_block_bwd(dy, x, img, n2w, n2b, f1b, None, 1, 1e-5, *gw))
     print(f"           MLP bwd fused {t_fb:.1f} us vs unfused {t_ub:.1f} us")
+
+# ---- attention half-block (B=2, 32^3 grid, C=48, 3 heads): fused vs the unfused kernel sequence of SelfBlockFn
+if C == 48 and T == 65536:
+    B_, D_ = 2, 32
+    xg = x.view(B_, D_, D_, D_, C)
+    u = lambda *s: ((torch.rand(*s, generator=g) * 2 - 1) * 0.3).to(dev)
+    qw, kvw, pw = u(C, C), u(2 * C, C), u(C, C)
+    qb, kvb, pb = torch.zeros(C, device=dev), torch.zeros(2 * C, device=dev), torch.zeros(C, device=dev)
+    aimg = fused.attn_images(qw, kvw, pw)
+    aimg.refresh()
+    src = torch.randn(B_, D_, D_, D_, C, generator=g).to(dev)
+    for cross in (False, True):
+        s_ = src if cross else None
+        t_f = timeit(lambda: fused.attn_block_fwd(xg, s_, aimg, n2w, n2b, qb, kvb, pb, None, 3, 1e-5))
+        names = (n2w, n2b, qw, qb, kvw, kvb, pw, pb)
+        gb = [torch.zeros_like(t) for t in names]
+        t_b = timeit(lambda: fused.attn_block_bwd(dy.view_as(xg), xg, s_, aimg, n2w, n2b, qb, kvb, None, 3, 1e-5, *gb))
+        print(f"           attention half ({'cross' if cross else 'self'}): fwd fused {t_f:.1f} us, bwd fused {t_b:.1f} us")

@@ -223,5 +223,7 @@ def test_fused_blocks_match_exact_path(cross, heads, dims, train):
     if cross:
         assert rel(dxa1, dxa0) < 2e-3          # through the TF32 tensor-core offset conv
     for k in g0:
-        tol = 5e-3 if ("conv_offset" in k or (cross and "norm1" in k)) else 1e-4
+        # a cross block's offset conv runs single-pass TF32 in mode 1 (1e-3 on the sampling positions), which moves k / v and
+        # with them every gradient of the block; the self block has no TF32 kernel left and matches the exact path to 1e-4
+        tol = 5e-3 if cross else 1e-4
         assert rel(g1[k], g0[k]) < tol, (k, rel(g1[k], g0[k]))
