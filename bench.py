@@ -273,6 +273,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout must carry exactly ONE JSON line: native libraries (the NCCL version banner) write to file descriptor 1
+    # directly, so fd 1 is pointed at stderr for the run and the line goes out through a saved duplicate
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -294,9 +299,11 @@ def run_ours(args):
     arena = None
     if args.arena == 1 or (args.arena < 0 and world > 1):
         from micformer_b200.arena import GradArena
-        arena = GradArena(model.parameters())      # .grad slices of one flat buffer: 1 memset, in-place all-reduce
+        arena = GradArena.for_model(model)         # .grad slices of one flat buffer ([decoder | encoder]): 1 memset, in-place all-reduce
         opt.attach_arena(arena)
     sync = GradSync(list(model.parameters()), arena=arena)
+    if arena is not None and world > 1 and os.environ.get("MICFORMER_OVERLAP", "1") != "0":
+        sync.enable_overlap(model)                 # decoder gradients are exchanged under the encoder's backward
     x_h, lab_h = O.synth_inputs(B, S, cfg.num_classes, seed=1 + rank)
     x_h, lab_h = x_h.pin_memory(), lab_h.pin_memory()
     x_d, lab_d = x_h.to(dev), lab_h.to(dev)
@@ -550,7 +557,8 @@ def run_ours(args):
             "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "attention_kernel": attn,
             "kernel_shares": shares, "secondary": secondary, "eager_cuda": eager,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly: drain, rendezvous once
         # more and leave without running destructors (every rank exits 0; rank 0 has already printed its line)

@@ -14,7 +14,12 @@ import torch
 
 
 class GradArena:
-    def __init__(self, params):
+    def __init__(self, params, segments=None):
+        """``segments``: optional list of parameter lists that partition ``params``; the flat buffer is laid out segment by
+        segment and ``self.segments`` holds their (start, end) offsets -- ``parallel.GradSync`` exchanges a segment as soon as
+        the backward pass has finished producing it (``for_model``)."""
+        if segments is not None:
+            params = [p for seg in segments for p in seg]
         ps = [p for p in params if p.requires_grad]
         if not ps:
             raise ValueError("GradArena: no trainable parameters")
@@ -27,12 +32,30 @@ class GradArena:
             n += (p.numel() + 63) // 64 * 64                 # 256-byte aligned slices (TMA reduce-add, float4 atomics)
         self.flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
         self.params = ps
+        self.segments = None
+        if segments is not None:
+            self.segments, k = [], 0
+            for seg in segments:
+                cnt = sum(1 for p in seg if p.requires_grad)
+                start = offs[k] if cnt else n
+                k += cnt
+                self.segments.append((start, offs[k] if k < len(offs) else n))
         self._views = []
         for p, o in zip(ps, offs):
             v = self.flat[o:o + p.numel()].view_as(p)
             p.grad = v
             p._mic_arena = True
             self._views.append(v)
+
+    @classmethod
+    def for_model(cls, head):
+        """Head / MicFormer: [decoder + tail | encoder] -- the backward pass finishes the decoder's gradients (up_layers,
+        concat_back_dim, norm2, reverse_patch_embedding, out_conv) when it reaches the bottleneck, long before the encoder's."""
+        dec, enc = [], []
+        for name, p in head.named_parameters():
+            n = name[5:] if name.startswith("swin.") else name
+            (dec if n.startswith(("up_layers.", "concat_back_dim.", "norm2.", "reverse_patch_embedding.", "out_conv.")) else enc).append(p)
+        return cls(None, segments=[dec, enc])
 
     def attached(self) -> bool:
         """every parameter still points into the arena (nobody called zero_grad(set_to_none=True))"""

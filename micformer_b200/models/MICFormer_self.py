@@ -577,6 +577,12 @@ class MicFormer(nn.Module):
             feats_f.append(fo)
         moving = ops.LayerNormFn.apply(moving, None, self.norm.weight, self.norm.bias)
         fixed = ops.LayerNormFn.apply(fixed, None, self.norm.weight, self.norm.bias)
+        hook = self.__dict__.get("_bottleneck_grad_hook")
+        if hook is not None and moving.requires_grad:
+            # data parallelism (parallel.GradSync.enable_overlap): when the backward pass arrives here the decoder's gradients
+            # are complete and their all-reduce can start under the encoder's backward
+            moving.register_hook(hook)
+            fixed.register_hook(hook)
         L = self.num_layers
         for inx, layer_up in enumerate(self.up_layers):
             if inx > 0:

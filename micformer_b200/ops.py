@@ -800,10 +800,11 @@ class PatchMergeFn(torch.autograd.Function):
         B, Dq, Hq, Wq, C, Co = ctx.meta
         R = B * Dq * Hq * Wq
         dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, Dq, Hq, Wq), beta=ctx.nb)
-        drows = linear_bwd_data(dz, Co, w2, R, Co, 8 * C)
-        dW, db = linear_bwd_weight(dz, Co, rows, 8 * C, R, Co, 8 * C)
-        dx = _empty((B, 2 * Dq, 2 * Hq, 2 * Wq, C), dz)
-        block_permute(drows, dx, B, Dq, Hq, Wq, 2, C, 8 * Dq * Hq * Wq * C, False)
+        with side_branch() as sb:
+            dW, db = linear_bwd_weight_side(sb, dz, Co, rows, 8 * C, R, Co, 8 * C)
+            drows = linear_bwd_data(dz, Co, w2, R, Co, 8 * C)
+            dx = _empty((B, 2 * Dq, 2 * Hq, 2 * Wq, C), dz)
+            block_permute(drows, dx, B, Dq, Hq, Wq, 2, C, 8 * Dq * Hq * Wq * C, False)
         return dx, dW, db, dnw, dnb
 
 
@@ -835,8 +836,9 @@ class PatchExpandFn(torch.autograd.Function):
         dz, _, dnw, dnb = ln_bwd(dy.contiguous(), z, None, nw, mean, rstd, None, None, (B, 2 * D, 2 * H, 2 * W), beta=ctx.nb)
         drows = _empty((T, 8 * Co), dz)
         block_permute(dz, drows, B, D, H, W, 2, Co, 8 * D * H * W * Co, True)
-        dx = linear_bwd_data(drows, 8 * Co, wk, T, 8 * Co, C, w_is_kn=True).view(x.shape)
-        dW, db8 = linear_bwd_weight(drows, 8 * Co, x, C, T, 8 * Co, C, w_is_kn=True)
+        with side_branch() as sb:
+            dW, db8 = linear_bwd_weight_side(sb, drows, 8 * Co, x, C, T, 8 * Co, C, w_is_kn=True)
+            dx = linear_bwd_data(drows, 8 * Co, wk, T, 8 * Co, C, w_is_kn=True).view(x.shape)
         return dx, dW, db8, dnw, dnb
 
 
@@ -914,18 +916,21 @@ class SegHeadFn(torch.autograd.Function):
         B, D, H, W, E, Ch, NC = ctx.meta
         T = B * D * H * W
         dlog = dlog.contiguous()
-        dy24 = torch.empty_like(y24)
-        conv3_bwd_data(dlog, wo, dy24, False, None, False, B, (4 * D, 4 * H, 4 * W), NC, True)
         n2b, bo = ctx.pb
-        dwo = torch.zeros_like(wo)
-        dbo = _acc(bo) if _acc(bo) is not None else _zeros((NC,), xm)
-        conv3_bwd_weight(dlog, y24, None, dwo, dbo, B, (4 * D, 4 * H, 4 * W), NC, True)
-        drows = _empty((T, 64 * Ch), xm)
-        block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
-        del dy24
-        dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
-        dwr, dbr64 = linear_bwd_weight(drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
-        dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W), beta=n2b)
+        with side_branch() as sb:
+            # the two weight-gradient kernels of the tail (1.1 + 0.25 ms at 128^3) feed nothing downstream: side branch
+            dwo = torch.zeros_like(wo)
+            dbo = _acc(bo) if _acc(bo) is not None else _zeros((NC,), xm)
+            sb.hold(dlog, y24)
+            sb.run(conv3_bwd_weight, dlog, y24, None, dwo, dbo, B, (4 * D, 4 * H, 4 * W), NC, True)
+            dy24 = torch.empty_like(y24)
+            conv3_bwd_data(dlog, wo, dy24, False, None, False, B, (4 * D, 4 * H, 4 * W), NC, True)
+            drows = _empty((T, 64 * Ch), xm)
+            block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
+            del dy24
+            dwr, dbr64 = linear_bwd_weight_side(sb, drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
+            dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
+            dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W), beta=n2b)
         return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, None, _gret(bo, dbo)
 
 

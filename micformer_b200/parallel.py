@@ -27,6 +27,37 @@ class GradSync:
             raise ValueError("GradSync: reduce must be 'mean' (per-rank loss, the reference semantics) or 'sum' "
                              "(MDiceLoss(process_group=...): the loss already spans the global batch)")
         self.reduce = reduce
+        self._early = None
+
+    # ---- overlap: exchange the decoder's gradients while the encoder's backward is still running --------------------
+    def enable_overlap(self, head) -> None:
+        """With a segmented arena (``GradArena.for_model``): the decoder segment is all-reduced asynchronously as soon as the
+        backward pass reaches the bottleneck (gradient hooks on the two ``norm`` outputs, installed by ``MicFormer._trunk``),
+        the encoder segment in ``sync()``.  Works eagerly and inside CUDA-graph capture (the collective becomes a parallel
+        branch of the graph)."""
+        if self.arena is None or not getattr(self.arena, "segments", None):
+            raise RuntimeError("GradSync.enable_overlap needs a segmented arena (GradArena.for_model)")
+        swin = head.swin if hasattr(head, "swin") else head
+        self._pending, self._early, self._hook_events = 0, None, []
+        swin.__dict__["_bottleneck_grad_hook"] = self._on_bottleneck_grad
+
+    def _on_bottleneck_grad(self, grad):
+        if self.world <= 1:
+            return grad
+        cur = torch.cuda.current_stream()
+        self._pending += 1
+        if self._pending < 2:                      # first of the two modality streams: remember where its backward stands
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._hook_events.append(ev)
+            return grad
+        for ev in self._hook_events:               # second one: both decoders' gradient kernels are enqueued
+            cur.wait_event(ev)
+        self._hook_events.clear()
+        self._pending = 0
+        a, b = self.arena.segments[0]
+        self._early = self._reduce_(self.arena.flat[a:b], async_op=True)
+        return grad
 
     @property
     def world(self) -> int:
@@ -70,7 +101,15 @@ class GradSync:
             return
         if self.arena is not None and self.arena.attached():
             # parameters without a gradient (concat_back_dim.0) hold zeros on every rank: harmless to include
-            self._reduce_(self.arena.flat)
+            early = getattr(self, "_early", None)
+            if early is not None:                  # decoder segment already in flight: finish it, exchange the rest
+                a, b = self.arena.segments[0]
+                rest = self.arena.flat[b:] if a == 0 else torch.cat([self.arena.flat[:a], self.arena.flat[b:]])
+                self._reduce_(rest)
+                early.wait()
+                self._early = None
+            else:
+                self._reduce_(self.arena.flat)
             return
         if self._plan is None:
             self._build_plan()

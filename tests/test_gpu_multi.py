@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, mode, global_dice, out):
+def _worker(rank, world, port, mode, global_dice, overlap, out):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     from micformer_b200 import _native as N
@@ -32,9 +32,11 @@ def _worker(rank, world, port, mode, global_dice, out):
     head.load_state_dict(sd, strict=True)
     head = head.cuda().eval()
     x, lab = O.synth_inputs(world, 64, cfg.num_classes, seed=21)
-    arena = GradArena(head.parameters())
+    arena = GradArena.for_model(head) if overlap else GradArena(head.parameters())
     crit = MDiceLoss(process_group=dist.group.WORLD if global_dice else None)
     sync = GradSync(list(head.parameters()), arena=arena, reduce=crit.grad_reduce)
+    if overlap:
+        sync.enable_overlap(head)          # decoder segment all-reduced from the bottleneck gradient hooks
     loss = crit(head(x[rank:rank + 1].cuda()), lab[rank:rank + 1].cuda())
     loss.backward()
     sync.sync()
@@ -45,8 +47,8 @@ def _worker(rank, world, port, mode, global_dice, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,global_dice", [(0, False), (0, True), (1, True)])
-def test_two_rank_gradients_match_single_process(tmp_path, mode, global_dice):
+@pytest.mark.parametrize("mode,global_dice,overlap", [(0, False, False), (0, True, True), (0, False, True), (1, True, True)])
+def test_two_rank_gradients_match_single_process(tmp_path, mode, global_dice, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -55,7 +57,7 @@ def test_two_rank_gradients_match_single_process(tmp_path, mode, global_dice):
     from micformer_b200.models.MICFormer_self import Head, MicFormer
     from oracle import micformer_oracle as O
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, mode, global_dice, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, mode, global_dice, overlap, out), nprocs=2, join=True)
     got = torch.load(out)
     # single process
     prev = N.get_gemm_mode()

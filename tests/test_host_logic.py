@@ -69,3 +69,19 @@ def test_fused_tail_algebra_design_artifact():
     for seed, dims in [(0, (3, 4, 5)), (1, (1, 2, 1)), (2, (2, 2, 2))]:
         err, nz = A.check(seed=seed, dims=dims)
         assert err < 1e-12 and nz == 216
+
+
+def test_segmented_arena_for_model():
+    """GradArena.for_model: [decoder + tail | encoder] segments partition the flat buffer; every parameter points into it"""
+    from micformer_b200.arena import GradArena
+    from micformer_b200.models.MICFormer_self import Head
+    h = Head(embed_dim=24, num_classes=8)
+    a = GradArena.for_model(h)
+    (d0, d1), (e0, e1) = a.segments
+    assert d0 == 0 and d1 == e0 and e1 == a.flat.numel() and a.attached()
+    base = a.flat.data_ptr()
+    for name, p in h.named_parameters():
+        off = (p.grad.data_ptr() - base) // 4
+        dec = name.startswith(("swin.up_layers.", "swin.concat_back_dim.", "swin.norm2.", "swin.reverse_patch_embedding.", "out_conv."))
+        assert (d0 <= off < d1) if dec else (e0 <= off < e1), name
+    assert sum(p.numel() for p in h.parameters()) <= a.flat.numel()
