@@ -212,6 +212,21 @@ int mic_attn_block_bwd(const float* x, const float* kvsrc, const float* dy, floa
                        const float* beta, const float* bq, const float* bkv, const void* const* imgs, const float* rowscale,
                        float* dgamma, float* dbeta, float* dWq, float* dbq, float* dWkv, float* dbkv, float* dWp, float* dbp,
                        int B, int D, int H, int W, int C, int heads, float scale, float eps, void* stream);
+/* The same MLP half-block for the deep stages (64 <= C <= 384, C % 8 == 0, HID = 4C): the work is split over 128-token
+ * tiles AND 64-unit hidden chunks (grid = tiles x HID/64), operands are streamed through shared-memory rings, and every CTA
+ * adds its partial product into y, which MUST BE ZERO on entry (chunk 0 adds the residual and the bias).  Images as for
+ * mic_mlp_block_fwd. */
+int mic_mlp_split_fwd(const float* x, float* y_zeroed, const float* gamma, const float* beta, const float* b1,
+                      const float* b2, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
+                      const float* rowscale, int rows_per_sample, int T, int C, int HID, float eps, void* stream);
+/* Backward of mic_mlp_split_fwd up to the LayerNorm: recomputes LN / fc1 / GELU per (tile, hidden chunk); dxn (T, C) -- the
+ * gradient w.r.t. LN(x), ZERO on entry -- and dW1, db1, dW2, db2 are accumulated atomically; mean / rstd (T) of the LayerNorm
+ * are written for mic_layernorm_bwd, which finishes the half-block: dx = dy + LN'(dxn), dgamma, dbeta.  Images: w1nk (fc1,
+ * N = 4C x K = C), w2kn (fc2 transposed, N = 4C x K = C), w1kn (fc1 transposed, N = C x K = 4C). */
+int mic_mlp_split_bwd(const float* dy, const float* x, float* dxn_zeroed, float* mean, float* rstd, const float* gamma,
+                      const float* beta, const float* b1, const void* w1nk_hi, const void* w1nk_lo, const void* w2kn_hi,
+                      const void* w2kn_lo, const void* w1kn_hi, const void* w1kn_lo, const float* rowscale, int rows_per_sample,
+                      float* dW1, float* db1, float* dW2, float* db2, int T, int C, int HID, float eps, void* stream);
 /* dynamic shared memory the fused MLP kernels need for this C (-1: not built) */
 int mic_mlp_block_smem(int C);
 

@@ -53,6 +53,8 @@ SIGNATURES = {
     "mic_mlp_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, F, P],
     "mic_mlp_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, F, P],
     "mic_mlp_block_smem": [I],
+    "mic_mlp_split_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, F, P],
+    "mic_mlp_split_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, P],
     "mic_attn_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, F, P],
     "mic_attn_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, F, P],
     "mic_crop_residual": [P, P, P, P, I, I, I, I, I, I, I, I, P],
@@ -149,12 +151,16 @@ COST = {
                                      4 * _prod(*a[15:19]) * a[19] * (3 if a[1] is not None else 2) + 32 * a[19] * a[19]),
     "mic_attn_block_bwd": lambda a: (_prod(*a[19:23]) * (24 * a[23] * a[23] + 80 * a[23]),
                                      4 * _prod(*a[19:23]) * a[23] * (5 if a[1] is not None else 3) + 64 * a[23] * a[23]),
+    "mic_mlp_split_fwd": lambda a: (16 * a[12] * a[13] * a[13], 8 * a[12] * a[13] + 4 * 8 * a[13] * a[13]),
+    "mic_mlp_split_bwd": lambda a: (40 * a[20] * a[21] * a[21], 12 * a[20] * a[21] + 4 * 16 * a[21] * a[21]),
     "mic_crop_residual": lambda a: (0, 12 * _prod(*a[4:8]) * a[11]),
     "mic_crop_residual_bwd": lambda a: (0, 4 * a[3] * (_prod(*a[4:7]) + _prod(*a[7:10])) * a[10]),
 }
 
 
 TAG = {
+    "mic_mlp_split_bwd": lambda a: f"T{a[20]}xC{a[21]}",
+    "mic_mlp_split_fwd": lambda a: f"T{a[12]}xC{a[13]}",
     "mic_attn_block_bwd": lambda a: f"T{a[19] * a[20] * a[21] * a[22]}xC{a[23]}",
     "mic_attn_block_fwd": lambda a: f"T{a[15] * a[16] * a[17] * a[18]}xC{a[19]}",
     "mic_mlp_block_fwd": lambda a: f"T{a[12]}xC{a[13]}",

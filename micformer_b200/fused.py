@@ -128,7 +128,15 @@ def ensure_current(img: Optional[WeightImages]) -> None:
 
 
 def mlp_supported(c: int, hid: int) -> bool:
-    return enabled() and c in FUSED_C and hid == 4 * c
+    """resident-weight kernels for C in FUSED_C (stage 0), hidden-split streaming kernels for 64 <= C <= 384 (stages 1-3)"""
+    return enabled() and hid == 4 * c and (c in FUSED_C or mlp_split(c))
+
+
+def mlp_split(c: int) -> bool:
+    """MICFORMER_FUSED_SPLIT=<min C> enables the hidden-split kernels for channel counts >= <min C> (0 / unset: off)"""
+    import os
+    lo = int(os.environ.get("MICFORMER_FUSED_SPLIT", "0") or 0)
+    return lo > 0 and max(lo, 64) <= c <= 384 and c % 8 == 0 and (4 * c) % 64 == 0
 
 
 def mlp_block_fwd(x: torch.Tensor, img: WeightImages, gamma, beta, b1, b2, rowscale: Optional[torch.Tensor], rps: int,
@@ -136,6 +144,11 @@ def mlp_block_fwd(x: torch.Tensor, img: WeightImages, gamma, beta, b1, b2, rowsc
     """y = x + rowscale * fc2(GELU(fc1(LN(x))));  x (..., C) contiguous fp32"""
     c = x.shape[-1]
     t = x.numel() // c
+    if c not in FUSED_C:          # deep stages: hidden-split kernel accumulates into a zeroed output
+        y = torch.zeros_like(x)
+        N.call("mic_mlp_split_fwd", N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta), N.ptr(b1), N.ptr(b2), img.hi("w1_nk"),
+               img.lo("w1_nk"), img.hi("w2_nk"), img.lo("w2_nk"), N.ptr(rowscale), int(rps), t, c, 4 * c, float(eps))
+        return y
     y = torch.empty_like(x)
     N.call("mic_mlp_block_fwd", N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta), N.ptr(b1), N.ptr(b2), img.hi("w1_nk"),
            img.lo("w1_nk"), img.hi("w2_nk"), img.lo("w2_nk"), N.ptr(rowscale), int(rps), t, c, float(eps))
@@ -201,3 +214,18 @@ def attn_block_bwd(dy: torch.Tensor, x: torch.Tensor, kvsrc: Optional[torch.Tens
            N.ptr(bkv), ctypes.cast(arr, ctypes.c_void_p), N.ptr(rowscale), N.ptr(dgamma), N.ptr(dbeta), N.ptr(dWq), N.ptr(dbq),
            N.ptr(dWkv), N.ptr(dbkv), N.ptr(dWp), N.ptr(dbp), b, d, h, w, c, heads, float(c // heads) ** -0.5, float(eps))
     return dx, dsrc
+
+
+def mlp_split_bwd(dy: torch.Tensor, x: torch.Tensor, img: WeightImages, gamma, beta, b1, rowscale: Optional[torch.Tensor],
+                  rps: int, eps: float, dW1, db1, dW2, db2):
+    """deep-stage MLP backward up to the LayerNorm: -> (dxn, mean, rstd); fc1 / fc2 gradients are ACCUMULATED.  The caller
+    finishes with the LayerNorm backward kernel (dx = dy + LN'(dxn), dgamma, dbeta)."""
+    c = x.shape[-1]
+    t = x.numel() // c
+    dxn = torch.zeros_like(x)
+    mean = torch.empty(t, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(t, device=x.device, dtype=torch.float32)
+    N.call("mic_mlp_split_bwd", N.ptr(dy), N.ptr(x), N.ptr(dxn), N.ptr(mean), N.ptr(rstd), N.ptr(gamma), N.ptr(beta), N.ptr(b1),
+           img.hi("w1_nk"), img.lo("w1_nk"), img.hi("w2_kn"), img.lo("w2_kn"), img.hi("w1_kn"), img.lo("w1_kn"),
+           N.ptr(rowscale), int(rps), N.ptr(dW1), N.ptr(db1), N.ptr(dW2), N.ptr(db2), t, c, 4 * c, float(eps))
+    return dxn, mean, rstd

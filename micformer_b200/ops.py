@@ -380,11 +380,18 @@ def _mlp_bwd(sb, dy, x1, saved, n2w, f1w, f2w, s2, dims, n2b=None, f1b=None, f2b
     T = B * D * H * W
     Hd = f1w.shape[0]
     rps = D * H * W
-    if img is not None:
+    if img is not None and C in F_.FUSED_C:
         ps = (n2w, n2b, f1w, f1b, f2w, f2b)
         gs = [_acc(p) if _acc(p) is not None else _zeros(tuple(p.shape), x1) for p in ps]
         dx1 = F_.mlp_block_bwd(dy, x1, img, n2w, n2b, f1b, s2, rps, LN_EPS, *gs)
         return (dx1, *[_gret(p, g) for p, g in zip(ps, gs)])
+    if img is not None:
+        # deep stages: hidden-split kernel (fc1 / fc2 gradients + d LN(x)), then the LayerNorm backward kernel
+        ps = (f1w, f1b, f2w, f2b)
+        gs = [_acc(p) if _acc(p) is not None else _zeros(tuple(p.shape), x1) for p in ps]
+        dxn, mean2, rstd2 = F_.mlp_split_bwd(dy, x1, img, n2w, n2b, f1b, s2, rps, LN_EPS, *gs)
+        dx1, _, dn2w, dn2b = ln_bwd(dxn, x1, None, n2w, mean2, rstd2, dy, None, dims, beta=n2b)
+        return (dx1, dn2w, dn2b, *[_gret(p, g) for p, g in zip(ps, gs)])
     df2w, df2b = linear_bwd_weight_side(sb, dy, C, h, Hd, T, C, Hd, wp=f2w, bp=f2b, rowscale=s2, rps=rps)
     dh = linear_bwd_data(dy, C, f2w, T, C, Hd, gelu_pre=hpre, rowscale=s2, rps=rps)
     df1w, df1b = linear_bwd_weight_side(sb, dh, Hd, xn2, C, T, Hd, C, wp=f1w, bp=f1b)

@@ -7,6 +7,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True)
+def _split_kernels_on(monkeypatch):
+    monkeypatch.setenv("MICFORMER_FUSED_SPLIT", "64")       # the deep-stage hidden-split kernels are opt-in
+
+
+@pytest.fixture(autouse=True)
 def _tensor_core_mode():
     """the fused kernels belong to gemm mode 1; the mode is process-global, so restore it for the other test modules"""
     from micformer_b200 import _native as N
@@ -35,7 +40,8 @@ def _mlp_ref64(x, p, rowscale=None, rps=1):
     return x + o
 
 
-@pytest.mark.parametrize("C,T", [(48, 128), (48, 1000), (24, 4096), (48, 65536)])
+@pytest.mark.parametrize("C,T", [(48, 128), (48, 1000), (24, 4096), (48, 65536), (96, 8192), (192, 1024), (384, 128), (192, 200),
+                                 (64, 130)])
 def test_fused_mlp_forward(C, T):
     from micformer_b200 import fused, _native as N
     dev = torch.device("cuda")
@@ -54,6 +60,35 @@ def test_fused_mlp_forward(C, T):
         ref2 = _mlp_ref64(x, p, rs, T // 2)
         assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) < 2e-5
         assert torch.equal(y2[: T // 2], x[: T // 2])          # dropped sample: the branch contributes exactly 0
+
+
+@pytest.mark.parametrize("C,T", [(96, 8192), (192, 1024), (384, 128), (192, 200), (64, 130)])
+def test_split_mlp_backward(C, T):
+    """deep-stage MLP half-block through ops._mlp_fwd / _mlp_bwd (hidden-split kernels + LayerNorm backward kernel)"""
+    from micformer_b200 import fused, ops
+    dev = torch.device("cuda")
+    x, p = _mlp_case(C, T, 5 + C + T, dev)
+    g = torch.Generator().manual_seed(99)
+    dy = torch.randn(T, C, generator=g).to(dev)
+    B = 2 if T % 2 == 0 else 1
+    rs = torch.tensor([0.5, 1.25][:B], device=dev) if B == 2 else None
+    img = fused.mlp_images(p["w1"], p["w2"])
+    img.refresh()
+    dims = (B, 1, 1, T // B)
+    xg = x.view(B, 1, 1, T // B, C)
+    y, saved = ops._mlp_fwd(xg, p["gamma"], p["beta"], p["w1"], p["b1"], p["w2"], p["b2"], rs, dims, img)
+    with ops.side_branch() as sb:
+        dx, dg, dbt, dw1, db1, dw2, db2 = ops._mlp_bwd(sb, dy.view_as(xg), xg, saved, p["gamma"], p["w1"], p["w2"], rs, dims,
+                                                         p["beta"], p["b1"], p["b2"], img)
+    x64 = x.double().requires_grad_(True)
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    yr = _mlp_ref64(x64, p64, rs, T // B)
+    yr.backward(dy.double())
+    rel = lambda a, b: float((a.double().reshape(b.shape) - b).norm() / (b.norm() + 1e-30))
+    assert rel(y, yr.detach()) < 2e-5
+    assert rel(dx, x64.grad) < 3e-5, rel(dx, x64.grad)
+    for got, k in ((dg, "gamma"), (dbt, "beta"), (dw1, "w1"), (db1, "b1"), (dw2, "w2"), (db2, "b2")):
+        assert rel(got, p64[k].grad) < 5e-5, (k, rel(got, p64[k].grad))
 
 
 @pytest.mark.parametrize("C,T", [(48, 128), (48, 1000), (24, 4096), (48, 65536)])
