@@ -227,6 +227,9 @@ int mic_mlp_split_bwd(const float* dy, const float* x, float* dxn_zeroed, float*
                       const float* beta, const float* b1, const void* w1nk_hi, const void* w1nk_lo, const void* w2kn_hi,
                       const void* w2kn_lo, const void* w1kn_hi, const void* w1kn_lo, const float* rowscale, int rows_per_sample,
                       float* dW1, float* db1, float* dW2, float* db2, int T, int C, int HID, float eps, void* stream);
+/* profiling hook: register (or clear with NULL) a device buffer of 4 x 8 x 32 uint64 that the fused kernels stamp with
+ * %globaltimer at their phase boundaries (scripts/trace_fused.py) */
+int mic_debug_t5_trace(void* buf);
 /* dynamic shared memory the fused MLP kernels need for this C (-1: not built) */
 int mic_mlp_block_smem(int C);
 

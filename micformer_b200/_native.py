@@ -53,6 +53,7 @@ SIGNATURES = {
     "mic_mlp_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, F, P],
     "mic_mlp_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, F, P],
     "mic_mlp_block_smem": [I],
+    "mic_debug_t5_trace": [P],
     "mic_mlp_split_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, F, P],
     "mic_mlp_split_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, P],
     "mic_attn_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, F, P],

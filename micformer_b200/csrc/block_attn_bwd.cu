@@ -34,6 +34,7 @@ struct AttnBwdCfg {
     static constexpr int T_Q = 0, T_K = CP, T_V = CP + C, T_DO = CP + 2 * C, T_DWP = 192, T_DWQ = 192 + NB, T_DWKV = 192 + 2 * NB;
     static_assert(T_DO + CP <= 192 && T_DWKV + NB <= 512 && NB <= 64, "TMEM budget / ones column inside the 64-feature panel");
     static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(C % 16 == 0 && C <= 64, "the chunked LayerNorm backward walks 16-column chunks (4 accumulators)");
     static_assert(W_A % 1024 == 0 && W_P % 1024 == 0 && WC % 1024 == 0, "swizzle alignment");
 };
 
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             const int64_t grow = wg.row_of((int64_t)t * 16 + (row >> 3), row & 7, a.nwin_total);
             const bool ok = grow >= 0;
             float mean = 0.f, rstd = 0.f;
+            const bool tr = threadIdx.x == 96 + 32;       // (warp 4: quarter 0, head 0, lane 0 stamps the phase trace)
+            if (tr) t5_trace(n, 0);
             {   // the next tile's rows start their way to L2 now
                 const int64_t gnext = t + (int)gridDim.x < a.ntiles ? wg.row_of((int64_t)(t + gridDim.x) * 16 + (row >> 3), row & 7, a.nwin_total) : -1;
                 if (gnext >= 0) {
@@ -243,9 +246,11 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(a_full);
+            if (tr) t5_trace(n, 1);
             // ---- q, k, v, do of (row, head)
             bar_wait(g1, n & 1);
             fence_after();
+            if (tr) t5_trace(n, 2);
             float qv[HD], kv_[HD], vv[HD], dov[HD];
             ld_cols<HD>(tmem + lane_base + K::T_Q + hh * HD, qv);
             ld_cols<HD>(tmem + lane_base + K::T_K + hh * HD, kv_);
@@ -310,6 +315,7 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(o_full);
+            if (tr) t5_trace(n, 3);
 #pragma unroll
             for (int d = 0; d < HD; ++d) dq[d] *= a.scale;           // q = scale * (Wq xn + bq)
             // ---- as key j: dk_j = sum_i dS_ij q_i,  dv_j = sum_i P_ij do_i  (P, dS transposed inside the window)
@@ -327,7 +333,9 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
                 }
             }
             // ---- dq / dk / dv -> operand tiles (they reuse the dy and o tiles: wait until dWp has read those)
+            if (tr) t5_trace(n, 4);
             bar_wait(dwp_done, n & 1);
+            if (tr) t5_trace(n, 5);
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
                 const int cq = (hh * HD) / 8 + c;                    // chunk of dq / dk inside [0, C); dv sits at C + ...
@@ -346,46 +354,60 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(dqkv_full);
+            if (tr) t5_trace(n, 6);
             // ---- tile end: dxn (and dsrc) complete
             bar_wait(g2, n & 1);
             fence_after();
+            if (tr) t5_trace(n, 7);
             if (hh == STG_X) {
-                float gx[CP];
-#pragma unroll
-                for (int c0 = 0; c0 < CP; c0 += 16) ld16(tmem + lane_base + K::T_Q + c0, gx + c0);
-                ld_wait();
-                float xh[C], dyr[C];
-                load_row<C>(a.x, grow, ok, xh);
-                load_row<C>(a.dy, grow, ok, dyr);
-#pragma unroll
-                for (int i = 0; i < C; ++i) { xh[i] = ok ? (xh[i] - mean) * rstd : 0.f; if (!ok) gx[i] = 0.f; }
+                // LayerNorm backward in 16-column chunks (two passes: the row means first), so that only a few dozen registers are
+                // live: the one-shot version spilled under the 128-register cap and took a third of the tile time
+                const float* xp = a.x + grow * C;
+                const float* dp_ = a.dy + grow * C;
                 float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < C; ++i) { const float d = gx[i] * sg[i]; m1 += d; m2 = fmaf(d, xh[i], m2); }
-                m1 *= (1.f / C); m2 *= (1.f / C);
-                if (ok) {
-                    float4* po = reinterpret_cast<float4*>(a.dx + grow * C);
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float gx[16];
+                    ld16(tmem + lane_base + K::T_Q + c0, gx);
+                    ld_wait();
+                    if (ok) {
 #pragma unroll
-                    for (int i = 0; i < C / 4; ++i) {
-                        float4 o;
-                        o.x = dyr[4 * i] + rstd * (gx[4 * i] * sg[4 * i] - m1 - xh[4 * i] * m2);
-                        o.y = dyr[4 * i + 1] + rstd * (gx[4 * i + 1] * sg[4 * i + 1] - m1 - xh[4 * i + 1] * m2);
-                        o.z = dyr[4 * i + 2] + rstd * (gx[4 * i + 2] * sg[4 * i + 2] - m1 - xh[4 * i + 2] * m2);
-                        o.w = dyr[4 * i + 3] + rstd * (gx[4 * i + 3] * sg[4 * i + 3] - m1 - xh[4 * i + 3] * m2);
-                        po[i] = o;
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c0 + i));
+                            const float d0 = gx[i] * sg[c0 + i], d1 = gx[i + 1] * sg[c0 + i + 1], d2 = gx[i + 2] * sg[c0 + i + 2],
+                                        d3 = gx[i + 3] * sg[c0 + i + 3];
+                            m1 += (d0 + d1) + (d2 + d3);
+                            m2 = fmaf(d0, (xv.x - mean) * rstd, m2); m2 = fmaf(d1, (xv.y - mean) * rstd, m2);
+                            m2 = fmaf(d2, (xv.z - mean) * rstd, m2); m2 = fmaf(d3, (xv.w - mean) * rstd, m2);
+                        }
                     }
                 }
+                m1 *= (1.f / C); m2 *= (1.f / C);
 #pragma unroll
-                for (int gq = 0; gq < (C + 31) / 32; ++gq) {
-                    float v[32], w[32];
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float gx[16], v[32];
+                    ld16(tmem + lane_base + K::T_Q + c0, gx);
+                    ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int i = gq * 32 + e;
-                        v[e] = i < C ? gx[i < C ? i : 0] * xh[i < C ? i : 0] : 0.f;
-                        w[e] = i < C ? gx[i < C ? i : 0] : 0.f;
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv4 = xv;
+                        if (ok) { xv = __ldg(reinterpret_cast<const float4*>(xp + c0 + i)); dv4 = __ldg(reinterpret_cast<const float4*>(dp_ + c0 + i)); }
+                        const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd, xh2 = (xv.z - mean) * rstd, xh3 = (xv.w - mean) * rstd;
+                        const float g0 = ok ? gx[i] : 0.f, g1_ = ok ? gx[i + 1] : 0.f, g2_ = ok ? gx[i + 2] : 0.f, g3 = ok ? gx[i + 3] : 0.f;
+                        if (ok) {
+                            float4 o;
+                            o.x = dv4.x + rstd * (g0 * sg[c0 + i] - m1 - xh0 * m2);
+                            o.y = dv4.y + rstd * (g1_ * sg[c0 + i + 1] - m1 - xh1 * m2);
+                            o.z = dv4.z + rstd * (g2_ * sg[c0 + i + 2] - m1 - xh2 * m2);
+                            o.w = dv4.w + rstd * (g3 * sg[c0 + i + 3] - m1 - xh3 * m2);
+                            *reinterpret_cast<float4*>(a.dx + grow * C + c0 + i) = o;
+                        }
+                        v[i] = g0 * xh0; v[i + 1] = g1_ * xh1; v[i + 2] = g2_ * xh2; v[i + 3] = g3 * xh3;      // dgamma terms
+                        v[16 + i] = g0; v[16 + i + 1] = g1_; v[16 + i + 2] = g2_; v[16 + i + 3] = g3;             // dbeta terms
                     }
-                    cacc0[gq] += warp_colsum32(v, lane);
-                    cacc1[gq] += warp_colsum32(w, lane);
+                    // lanes 0..15 end up with the dgamma column sums of this chunk, lanes 16..31 with the dbeta ones
+                    const float cs = warp_colsum32(v, lane);
+                    if (c0 == 0) cacc0[0] += cs; else if (c0 == 16) cacc0[1] += cs; else if (c0 == 32) cacc1[0] += cs; else cacc1[1] += cs;
                 }
             } else if (hh == STG_DY && cross) {
                 float gs[CP];
@@ -399,12 +421,17 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
                 }
             }
             fence_before();
+            if (tr) t5_trace(n, 8);
         }
+        if (threadIdx.x == 96 + 32) t5_trace(7, 0);
         // ---------------- flush
+        if (hh == STG_X) {                   // chunk k of 16 columns: lanes 0..15 hold dgamma, lanes 16..31 dbeta
+            const float accs[4] = {cacc0[0], cacc0[1], cacc1[0], cacc1[1]};
 #pragma unroll
-        for (int gq = 0; gq < (C + 31) / 32; ++gq) {
-            const int col = gq * 32 + lane;
-            if (col < C && hh == STG_X) { atomicAdd(a.dgamma + col, cacc0[gq]); atomicAdd(a.dbeta + col, cacc1[gq]); }
+            for (int k = 0; k < 4; ++k) {
+                const int col = 16 * k + (lane & 15);
+                if (16 * k < C && col < C) atomicAdd((lane < 16 ? a.dgamma : a.dbeta) + col, accs[k]);
+            }
         }
         {
             // weight-gradient accumulators: rows = output feature (TMEM lane), columns 0..C-1 = input feature, column CP = the
@@ -430,6 +457,7 @@ __global__ void __launch_bounds__(AttnBwdCfg<C, HD>::THREADS, 1) attn_block_bwd_
             }
         }
     }
+    if (threadIdx.x == 96 + 32) t5_trace(7, 1);
     fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -458,6 +486,11 @@ static int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
 }  // namespace mic
 
 using namespace mic;
+
+extern "C" int mic_debug_t5_trace(void* buf) {       // phase trace of the attention backward kernel (this translation unit)
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(mic::t5::g_t5_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
 
 extern "C" int mic_attn_block_bwd(const float* x, const float* kvsrc, const float* dy, float* dx, float* dkvsrc,
                                   const float* gamma, const float* beta, const float* bq, const float* bkv, const void* const* imgs,

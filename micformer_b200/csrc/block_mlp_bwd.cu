@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
             sb1[i] = v;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        float cacc0[2] = {0.f, 0.f}, cacc1[2] = {0.f, 0.f};     // half 0: dgamma, dbeta;  half 1: db2, (unused)
+        float cacc0[2] = {0.f, 0.f};                                // half 1: db2 partial sums
+        float lnacc[4] = {0.f, 0.f, 0.f, 0.f};                      // half 0: per 16-column chunk, lanes 0..15 dgamma / 16..31 dbeta
         constexpr int NCHK = CP / 8;
         uint32_t g = 0, n = 0;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++n) {
@@ -298,52 +299,56 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
             bar_wait(g2_done, (g - 1) & 1);
             fence_after();
             if (half == 0) {
-                float gx[CP];
-#pragma unroll
-                for (int c0 = 0; c0 < CP; c0 += 16) ld16(tmem + lane_base + K::T_DXN + c0, gx + c0);
-                ld_wait();
-                float xh[C], dyr[C];
-                if (ok) {
-                    const float4* px = reinterpret_cast<const float4*>(a.x + grow * C);
-                    const float4* pd = reinterpret_cast<const float4*>(a.dy + grow * C);
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) {
-                        const float4 v = __ldg(px + i), d = __ldg(pd + i);
-                        xh[4 * i] = (v.x - mean) * rstd; xh[4 * i + 1] = (v.y - mean) * rstd;
-                        xh[4 * i + 2] = (v.z - mean) * rstd; xh[4 * i + 3] = (v.w - mean) * rstd;
-                        dyr[4 * i] = d.x; dyr[4 * i + 1] = d.y; dyr[4 * i + 2] = d.z; dyr[4 * i + 3] = d.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < C; ++i) { xh[i] = 0.f; dyr[i] = 0.f; gx[i] = 0.f; }
-                }
+                // LayerNorm backward in 16-column chunks, two passes (row means first): few live registers, no spills
+                const float* xp = a.x + grow * C;
+                const float* dp_ = a.dy + grow * C;
                 float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < C; ++i) { const float d = gx[i] * sg[i]; m1 += d; m2 = fmaf(d, xh[i], m2); }
-                m1 *= (1.f / C); m2 *= (1.f / C);
-                if (ok) {
-                    float4* po = reinterpret_cast<float4*>(a.dx + grow * C);
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float gx[16];
+                    ld16(tmem + lane_base + K::T_DXN + c0, gx);
+                    ld_wait();
+                    if (ok) {
 #pragma unroll
-                    for (int i = 0; i < C / 4; ++i) {
-                        float4 o;
-                        o.x = dyr[4 * i] + rstd * (gx[4 * i] * sg[4 * i] - m1 - xh[4 * i] * m2);
-                        o.y = dyr[4 * i + 1] + rstd * (gx[4 * i + 1] * sg[4 * i + 1] - m1 - xh[4 * i + 1] * m2);
-                        o.z = dyr[4 * i + 2] + rstd * (gx[4 * i + 2] * sg[4 * i + 2] - m1 - xh[4 * i + 2] * m2);
-                        o.w = dyr[4 * i + 3] + rstd * (gx[4 * i + 3] * sg[4 * i + 3] - m1 - xh[4 * i + 3] * m2);
-                        po[i] = o;
+                        for (int i = 0; i < 16; i += 4) {
+                            if (c0 + i < C) {
+                                const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c0 + i));
+                                const float d0 = gx[i] * sg[c0 + i], d1 = gx[i + 1] * sg[c0 + i + 1], d2 = gx[i + 2] * sg[c0 + i + 2],
+                                            d3 = gx[i + 3] * sg[c0 + i + 3];
+                                m1 += (d0 + d1) + (d2 + d3);
+                                m2 = fmaf(d0, (xv.x - mean) * rstd, m2); m2 = fmaf(d1, (xv.y - mean) * rstd, m2);
+                                m2 = fmaf(d2, (xv.z - mean) * rstd, m2); m2 = fmaf(d3, (xv.w - mean) * rstd, m2);
+                            }
+                        }
                     }
                 }
+                m1 *= (1.f / C); m2 *= (1.f / C);
 #pragma unroll
-                for (int gq = 0; gq < (C + 31) / 32; ++gq) {
-                    float v[32], w[32];
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float gx[16], v[32];
+                    ld16(tmem + lane_base + K::T_DXN + c0, gx);
+                    ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int i = gq * 32 + e;
-                        v[e] = i < C ? gx[i < C ? i : 0] * xh[i < C ? i : 0] : 0.f;
-                        w[e] = i < C ? gx[i < C ? i : 0] : 0.f;
+                    for (int i = 0; i < 16; i += 4) {
+                        const bool in = ok && (c0 + i < C);
+                        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv4 = xv;
+                        if (in) { xv = __ldg(reinterpret_cast<const float4*>(xp + c0 + i)); dv4 = __ldg(reinterpret_cast<const float4*>(dp_ + c0 + i)); }
+                        const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd, xh2 = (xv.z - mean) * rstd, xh3 = (xv.w - mean) * rstd;
+                        const float g0 = in ? gx[i] : 0.f, g1_ = in ? gx[i + 1] : 0.f, g2_ = in ? gx[i + 2] : 0.f, g3 = in ? gx[i + 3] : 0.f;
+                        if (in) {
+                            const int ci = (c0 + i) < C ? c0 + i : 0;
+                            float4 o;
+                            o.x = dv4.x + rstd * (g0 * sg[ci] - m1 - xh0 * m2);
+                            o.y = dv4.y + rstd * (g1_ * sg[ci + 1] - m1 - xh1 * m2);
+                            o.z = dv4.z + rstd * (g2_ * sg[ci + 2] - m1 - xh2 * m2);
+                            o.w = dv4.w + rstd * (g3 * sg[ci + 3] - m1 - xh3 * m2);
+                            *reinterpret_cast<float4*>(a.dx + grow * C + c0 + i) = o;
+                        }
+                        v[i] = g0 * xh0; v[i + 1] = g1_ * xh1; v[i + 2] = g2_ * xh2; v[i + 3] = g3 * xh3;      // dgamma terms
+                        v[16 + i] = g0; v[16 + i + 1] = g1_; v[16 + i + 2] = g2_; v[16 + i + 3] = g3;             // dbeta terms
                     }
-                    cacc0[gq] += warp_colsum32(v, lane);
-                    cacc1[gq] += warp_colsum32(w, lane);
+                    const float cs = warp_colsum32(v, lane);      // lanes 0..15: dgamma of this chunk, lanes 16..31: dbeta
+                    if (c0 == 0) lnacc[0] += cs; else if (c0 == 16) lnacc[1] += cs; else if (c0 == 32) lnacc[2] += cs; else lnacc[3] += cs;
                 }
             }
             fence_before();
@@ -352,9 +357,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1) mlp_block_bwd_kernel(const MlpB
 #pragma unroll
         for (int gq = 0; gq < (C + 31) / 32; ++gq) {
             const int col = gq * 32 + lane;
-            if (col < C) {
-                if (half == 0) { atomicAdd(a.dgamma + col, cacc0[gq]); atomicAdd(a.dbeta + col, cacc1[gq]); }
-                else atomicAdd(a.db2 + col, cacc0[gq]);
+            if (col < C && half == 1) atomicAdd(a.db2 + col, cacc0[gq]);
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = 16 * k + (lane & 15);
+                if (16 * k < C && col < C) atomicAdd((lane < 16 ? a.dgamma : a.dbeta) + col, lnacc[k]);
             }
         }
         if (q < 2) {                      // accumulator rows 0..63 = hidden index inside the chunk (rows 64..127 are not used)

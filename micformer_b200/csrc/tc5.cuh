@@ -19,6 +19,18 @@ namespace t5 {
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// optional phase trace (debug / profiling scripts): when a buffer is registered (mic_debug_t5_trace), the calling thread
+// stamps %globaltimer into slot `slot` of record `rec` (32 u64 slots per record) of CTA blockIdx.x (first 4 CTAs only)
+static __device__ unsigned long long* g_t5_trace = nullptr;      // (one copy per translation unit; no -rdc)
+__device__ __forceinline__ void t5_trace(int rec, int slot) {
+    unsigned long long* t = g_t5_trace;
+    if (t && blockIdx.x < 4 && blockIdx.y == 0 && rec < 8) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        t[(blockIdx.x * 8 + rec) * 32 + slot] = now;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));

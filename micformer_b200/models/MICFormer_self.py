@@ -386,6 +386,9 @@ class PatchMerging(nn.Module):
 
     def forward(self, x):
         w2 = self.down_conv.weight.permute(0, 2, 3, 4, 1).reshape(2 * self.dim, 8 * self.dim).contiguous()
+        B, D, H, W, C = x.shape
+        if (D % 2) or (H % 2) or (W % 2):       # odd sizes: one zero plane on the trailing side (M:551-555); torch plumbing
+            x = torch.nn.functional.pad(x, (0, 0, 0, W % 2, 0, H % 2, 0, D % 2))
         return ops.PatchMergeFn.apply(x.contiguous(), w2, self.down_conv.bias, self.norm.weight, self.norm.bias)
 
 
@@ -560,6 +563,9 @@ class MicFormer(nn.Module):
     def _trunk(self, vol):
         """Everything up to (not including) cat -> norm2 -> reverse_patch_embedding; vol is (B, 2, D, H, W)."""
         self._predraw_drop_path(vol.shape[0], vol.device)
+        D0, H0, W0 = vol.shape[2:]
+        if (D0 % 4) or (H0 % 4) or (W0 % 4):    # PatchEmbed3D pads to a multiple of the patch size (M:864-869); torch plumbing
+            vol = torch.nn.functional.pad(vol, (0, (4 - W0 % 4) % 4, 0, (4 - H0 % 4) % 4, 0, (4 - D0 % 4) % 4)).contiguous()
         # the optimizer changed the weights since the last forward: rebuild all fused-kernel weight images in one launch
         imgs = [m.fused_images() for m in self.modules() if isinstance(m, Mlp)]
         if fused.enabled() and vol.is_cuda:
@@ -588,8 +594,12 @@ class MicFormer(nn.Module):
             if inx > 0:
                 skip_m, skip_f = feats_m[L - 1 - inx], feats_f[L - 1 - inx]   # reference hard-codes 3 - inx (M:1018-1028)
                 if moving.shape != skip_m.shape:
-                    raise RuntimeError("micformer_b200: odd-size trilinear resize branch (M:1018-1025) is not built "
-                                       "(SURVEY 8f rank 4); use volumes divisible by 32")
+                    # odd sizes (volumes not divisible by 32): the up-sampled map is resized to the skip's grid, trilinear with
+                    # align_corners=True (M:1018-1025).  Rare validation-time branch: torch's interpolate (plumbing), not a kernel
+                    size = tuple(skip_m.shape[1:4])
+                    rs = lambda t: torch.nn.functional.interpolate(t.permute(0, 4, 1, 2, 3), size=size, mode="trilinear",
+                                                                   align_corners=True).permute(0, 2, 3, 4, 1).contiguous()
+                    moving, fixed = rs(moving), rs(fixed)
                 lin = self.concat_back_dim[inx]
                 moving = ops.SkipLinearFn.apply(moving, skip_m, lin.weight, lin.bias)
                 fixed = ops.SkipLinearFn.apply(fixed, skip_f, lin.weight, lin.bias)

@@ -757,7 +757,7 @@ class PatchEmbedFn(torch.autograd.Function):
         N.check_cuda_f32(vol, w, b)
         B, Cin, D, H, W = vol.shape
         if D % 4 or H % 4 or W % 4:
-            raise RuntimeError("PatchEmbed3D: sizes not divisible by 4 need the pad branch (SURVEY 8f rank 4): unsupported")
+            raise RuntimeError("PatchEmbedFn takes sizes divisible by 4: MicFormer._trunk zero-pads the volume first (M:864-869)")
         Dq, Hq, Wq = D // 4, H // 4, W // 4
         E = w.shape[0]
         rows = _empty((B * Dq * Hq * Wq, 64), vol)
@@ -787,7 +787,7 @@ class PatchMergeFn(torch.autograd.Function):
         N.check_cuda_f32(x, w2, b, nw, nb)
         B, D, H, W, C = x.shape
         if D % 2 or H % 2 or W % 2:
-            raise RuntimeError("PatchMerging: odd sizes need the pad branch (SURVEY 8f rank 4): unsupported")
+            raise RuntimeError("PatchMergeFn takes even sizes: PatchMerging.forward zero-pads odd ones first (M:551-555)")
         Dq, Hq, Wq = D // 2, H // 2, W // 2
         R = B * Dq * Hq * Wq
         Co = w2.shape[0]

@@ -342,8 +342,12 @@ def cross_block(x, xa, p, pre, heads, window, dp=0.0, training=False, gen=None, 
 
 
 def patch_merging(x: Tensor, p, pre: str) -> Tensor:
-    """M:542-561 (even sizes only; odd-size pad branch M:551-555 is SURVEY §8f rank 4)."""
-    y = F.conv3d(x.permute(0, 4, 1, 2, 3), p[f"{pre}.down_conv.weight"], p[f"{pre}.down_conv.bias"], stride=2)
+    """M:542-561, incl. the odd-size branch M:551-555: odd D/H/W are zero-padded by one on the trailing side."""
+    B, D, H, W, C = x.shape
+    xc = x.permute(0, 4, 1, 2, 3)
+    if (D % 2) or (H % 2) or (W % 2):
+        xc = F.pad(xc, (0, W % 2, 0, H % 2, 0, D % 2))
+    y = F.conv3d(xc, p[f"{pre}.down_conv.weight"], p[f"{pre}.down_conv.bias"], stride=2)
     return layer_norm(y.permute(0, 2, 3, 4, 1), p[f"{pre}.norm.weight"], p[f"{pre}.norm.bias"])
 
 
@@ -377,6 +381,10 @@ def micformer_forward(moving: Tensor, fixed: Tensor, p, cfg: Config, training=Fa
     L = cfg.num_layers
     dpr = cfg.drop_path_rates()
     w, b = p["swin.patch_embed.proj.weight"], p["swin.patch_embed.proj.bias"]
+    D0, H0, W0 = moving.shape[2:]
+    if (D0 % 4) or (H0 % 4) or (W0 % 4):          # PatchEmbed3D pads to a multiple of the patch size on the trailing side, M:864-869
+        pads = (0, (4 - W0 % 4) % 4, 0, (4 - H0 % 4) % 4, 0, (4 - D0 % 4) % 4)
+        moving, fixed = F.pad(moving, pads), F.pad(fixed, pads)
     moving = F.conv3d(moving, w, b, stride=4).permute(0, 2, 3, 4, 1).contiguous()   # M:871, M:1001
     fixed = F.conv3d(fixed, w, b, stride=4).permute(0, 2, 3, 4, 1).contiguous()
     feats_m, feats_f = [], []
@@ -392,7 +400,10 @@ def micformer_forward(moving: Tensor, fixed: Tensor, p, cfg: Config, training=Fa
     for k, i in enumerate(reversed(range(L))):
         if k > 0:
             skip_m, skip_f = feats_m[L - 1 - k], feats_f[L - 1 - k]
-            assert moving.shape == skip_m.shape, "odd-size interpolate branch (M:1018-1025) is out of scope"
+            if moving.shape != skip_m.shape:      # odd sizes: trilinear resize (align_corners=True) to the skip's grid, M:1018-1025
+                size = tuple(skip_m.shape[1:4])
+                moving = F.interpolate(moving.permute(0, 4, 1, 2, 3), size=size, mode="trilinear", align_corners=True).permute(0, 2, 3, 4, 1)
+                fixed = F.interpolate(fixed.permute(0, 4, 1, 2, 3), size=size, mode="trilinear", align_corners=True).permute(0, 2, 3, 4, 1)
             wcb, bcb = p[f"swin.concat_back_dim.{k}.weight"], p[f"swin.concat_back_dim.{k}.bias"]
             moving = F.linear(torch.cat([moving, skip_m], -1), wcb, bcb)
             fixed = F.linear(torch.cat([fixed, skip_f], -1), wcb, bcb)

@@ -146,3 +146,30 @@ def test_config4_attention_4096_windows():
                 assert float((lse[w * 343:(w + 1) * 343, h].double() - torch.logsumexp(s, -1)).abs().max()) < 3e-3
     finally:
         N.set_gemm_mode(prev)
+
+
+def test_odd_size_branches():
+    """a 70 x 72 x 66 volume (PatchEmbed3D / PatchMerging zero padding M:864-869, 551-555, trilinear
+    align_corners=True resize of the decoder maps M:1018-1025, windows padded on the odd grids) through the CUDA path vs the
+    oracle (itself pinned to the unmodified reference on this shape by tests/test_oracle_golden.py)."""
+    import dataclasses
+    from micformer_b200 import _native as N
+    from micformer_b200.loss.dice import MDiceLoss
+    prev = N.get_gemm_mode()
+    N.set_gemm_mode(0)
+    try:
+        cfg = dataclasses.replace(O.TRAIN, embed_dim=24)
+        sd = O.synth_state_dict(cfg, seed=5)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(1, 2, 70, 72, 66, generator=g)
+        lab = torch.nn.functional.one_hot(torch.randint(0, 8, (1, 72, 72, 68), generator=g), 8).permute(0, 4, 1, 2, 3).float()
+        head = _head(cfg, sd)
+        y = head(x.cuda())
+        assert tuple(y.shape) == (1, 8, 72, 72, 68)
+        loss = MDiceLoss()(y, lab.cuda())
+        loss.backward()
+        logits, loss_ref, grads = O.train_step(x, lab, sd, cfg)
+        assert abs(float(loss.detach()) - float(loss_ref)) < 2e-6
+        _compare(head, y, grads, logits, 1e-5, 1e-3, 2e-2)
+    finally:
+        N.set_gemm_mode(prev)

@@ -122,3 +122,33 @@ def test_oracle_equals_live_reference_train64():
         y_or = O.head_forward(x, head.state_dict(), O.TRAIN)
     assert max_rel(y_or, y_ref) < 5e-6
     assert max_rel(y_or[:, :, ::8, ::8, ::8], VEC["train64/logits_sub"]) < 5e-6
+
+
+@pytest.mark.reference
+def test_oracle_equals_live_reference_on_odd_sizes():
+    """PatchEmbed3D / PatchMerging padding (M:864-869, 551-555) and the decoder's trilinear resize
+    (M:1018-1025) -- a 70 x 72 x 66 volume pads to 72 x 72 x 68, stages 18x18x17 -> 9x9x9 -> 5^3 -> 3^3, and every skip
+    connection but the first needs the resize.  Forward and gradients of the restatement vs the unmodified reference."""
+    import dataclasses
+    from _reference_loader import reference_available, load_reference
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    ref_models, ref_loss = load_reference()
+    torch.manual_seed(0)
+    m = ref_models.Head(embed_dim=24, num_classes=8).eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 2, 70, 72, 66, generator=g)
+    y = m(x)
+    assert tuple(y.shape) == (1, 8, 72, 72, 68)
+    lab = torch.nn.functional.one_hot(torch.randint(0, 8, (1, 72, 72, 68), generator=g), 8).permute(0, 4, 1, 2, 3).float()
+    ref_loss.MDiceLoss()(y, lab).backward()
+    cfg = dataclasses.replace(O.TRAIN, embed_dim=24)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    logits, loss, grads = O.train_step(x, lab, sd, cfg)
+    assert float((logits - y.detach()).abs().max() / y.detach().abs().max()) < 1e-5
+    gl2 = float(sum((p.grad.double() ** 2).sum() for p in m.parameters() if p.grad is not None) ** 0.5)
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            assert grads[k] is None, k
+        else:
+            assert float((grads[k] - p.grad).norm() / (p.grad.norm() + 1e-6 * gl2)) < 1e-3, k
