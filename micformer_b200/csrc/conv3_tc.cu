@@ -13,10 +13,16 @@
 // (next 4-channel group).  One tcgen05.mma (M=128, N=NT, K=8 tf32) per (tap, chunk); the Dz output planes of
 // the segment accumulate in Dz*NT TMEM columns across all channel chunks.
 //
-// Producers (4 warps) move every 16-byte element with cp.async (zero-fill outside the volume), five plane-chunks
-// ahead of the one being finished, then round their own elements to nearest TF32 in shared memory (the tensor core
-// truncates) and publish the plane through an mbarrier; the MMA issuer is one elected lane of warp 4; the producer
-// warps drain TMEM at the end.  Small grids are split over channel chunks (grid.z) with an atomic epilogue.
+// Producers (4 warps): channels-last inputs arrive by TMA -- one 5-D box {4 channels, 10 x, 18 y, 1 z, 1 b} per 4-channel
+// group lands the haloed plane in exactly the layout above, out-of-volume positions zero-filled by the TMA unit (round 1
+// moved every 16-byte element with cp.async: 360 requests per plane-chunk, L1 request-rate bound at 5-9 us per plane;
+// that path remains for NCDHW inputs, whose channels are not contiguous).  The producer threads then round their own
+// elements to nearest TF32 in shared memory (the tensor core truncates) and publish the plane through an mbarrier; the
+// MMA issuer is one elected lane of warp 4; the producer warps drain TMEM at the end.  Small grids are split over channel
+// chunks (grid.z) with an atomic epilogue.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace mic {
@@ -26,7 +32,8 @@ constexpr int HXS = TX + 2, HYS = TY + 2;      // haloed plane
 constexpr int PPOS = HXS * HYS;                // 180 positions per staged plane
 constexpr int KJ = 2;                          // 4-channel groups per K chunk (8 input channels = one MMA K step)
 constexpr int CCH = 4 * KJ;
-constexpr int PLANE_BYTES = KJ * PPOS * 16;    // 5760
+constexpr int SLAB = (PPOS * 16 + 127) / 128 * 128;   // one 4-channel group of a plane: 2880 B padded to 2944 (TMA wants 128-byte aligned destinations)
+constexpr int PLANE_BYTES = KJ * SLAB;         // 5888
 constexpr int RING = 8;
 constexpr int AHEAD = RING - 3;                // plane-chunks in flight ahead of the one being published
 constexpr int PL = (PPOS * KJ + 127) / 128;    // 16-byte elements per producer thread per plane-chunk (3)
@@ -51,7 +58,17 @@ struct ConvTcGeom {
     int in_ncdhw, out_ncdhw, flip;
     int Dz, nseg, nfy, nfx;
     int ksplit, cps;       // channel-chunk splits (grid.z) and chunks per split; ksplit > 1 -> atomic epilogue
+    int use_tma;           // channels-last inputs with 8-channel-aligned tensors: planes are loaded by TMA boxes
 };
+
+__device__ __forceinline__ void ctma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void cbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ uint32_t csmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cbar_init(uint64_t* bar, uint32_t count) {
@@ -111,7 +128,8 @@ __device__ __forceinline__ void round_smem16(uint8_t* p) {
 
 template <int NT>
 __global__ void __launch_bounds__(CT_THREADS, NT == 16 ? 3 : 2)
-conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ Wsrc,
+conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ Wsrc,
                 const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, ConvTcGeom g, int tcols) {
     constexpr int W_BYTES = 27 * KJ * NT * 16;
     constexpr int WL = (27 * NT * KJ + 127) / 128;         // 16-byte weight elements per producer thread per chunk
@@ -123,7 +141,8 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     uint64_t* wfull = pempty + RING;
     uint64_t* wempty = wfull + 2;
     uint64_t* accdone = wempty + 2;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(accdone + 1);
+    uint64_t* pland = accdone + 1;                         // [RING] TMA plane landed (tx bytes)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(pland + RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Cin = g.C0 + g.C1;
@@ -145,7 +164,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
     const int64_t S = (int64_t)g.D * g.H * g.W;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RING; ++s) { cbar_init(&pfull[s], 128); cbar_init(&pempty[s], 1); }
+        for (int s = 0; s < RING; ++s) { cbar_init(&pfull[s], 128); cbar_init(&pempty[s], 1); cbar_init(&pland[s], 1); }
         for (int s = 0; s < 2; ++s) { cbar_init(&wfull[s], 128); cbar_init(&wempty[s], 1); }
         cbar_init(accdone, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,7 +189,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
         for (int i = 0; i < PL; ++i) {
             const int e = tid + i * 128;
             const int kj = e % KJ, pos = e / KJ;
-            e_off[i] = e < PPOS * KJ ? (kj * PPOS + pos) * 16 : -1;
+            e_off[i] = e < PPOS * KJ ? kj * SLAB + pos * 16 : -1;
             e_dy[i] = yb + pos / HXS - 1;
             e_dx[i] = xb + pos % HXS - 1;
         }
@@ -184,6 +203,19 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
             if (tid == 0) ctrace(0, n);                          // slot free, copies of plane-chunk n issued
             const bool zok = z >= 0 && z < g.D;
             const uint32_t sbase = ring_u32 + slot * PLANE_BYTES;
+            if (g.use_tma) {
+                // one box per 4-channel group: {4 c, 10 x, 18 y, 1 z, 1 b} at (c, xb-1, yb-1, z, b); the TMA unit zero-fills
+                // everything outside the tensor (the conv padding, and the whole plane for z = -1 / D)
+                if (tid == 0) {
+                    cbar_expect_tx(&pland[slot], KJ * PPOS * 16);
+#pragma unroll
+                    for (int kj = 0; kj < KJ; ++kj) {
+                        const int c = c0 + kj * 4;
+                        if (c < g.C0) ctma_load_5d(sbase + kj * SLAB, &map0, &pland[slot], c, xb - 1, yb - 1, z, b);
+                        else ctma_load_5d(sbase + kj * SLAB, &map1, &pland[slot], c - g.C0, xb - 1, yb - 1, z, b);
+                    }
+                }
+            } else
 #pragma unroll
             for (int i = 0; i < PL; ++i) {
                 if (e_off[i] < 0) continue;
@@ -228,9 +260,10 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
             else asm volatile("cp.async.commit_group;" ::: "memory");
         }
         for (int n = 0; n < total; ++n) {
-            // groups committed so far: ahead + n; plane-chunk n is group n
+            // groups committed so far: ahead + n; plane-chunk n is group n (with TMA planes the groups carry only the weights)
             if (ahead == AHEAD) asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
             else asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 2) : "memory");
+            if (g.use_tma) cbar_wait(&pland[n % RING], (n / RING) & 1);
             if (tid == 0) ctrace(1, n);                          // plane-chunk n landed (this thread's part)
             const int ch = n / ppc, pz = n - ch * ppc;
             const int slot = n % RING;
@@ -344,7 +377,7 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
 #pragma unroll
                         for (int tx = 0; tx < 3; ++tx) {
                             const int tap = (tz * 3 + ty) * 3 + tx;
-                            const uint64_t ad = cdesc(pbase + (uint32_t)((ty * HXS + tx) * 16), PPOS * 16, HXS * 16);
+                            const uint64_t ad = cdesc(pbase + (uint32_t)((ty * HXS + tx) * 16), SLAB, HXS * 16);
                             const uint64_t bd = cdesc(w_addr + (uint32_t)(wb * W_BYTES + tap * KJ * NT * 16), NT * 16, 128);
                             cmma(dcol, ad, bd, idesc, (ch | tap) ? 1u : 0u);
                         }
@@ -365,6 +398,34 @@ conv3_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tcols));
     }
+}
+
+typedef CUresult (*ConvEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ConvEncodeFn conv_get_encode() {
+    static ConvEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<ConvEncodeFn>(p);
+    }
+    return fn;
+}
+// channels-last (B, D, H, W, C) fp32 tensor as a 5-D map, box {4 c, 10 x, 18 y, 1, 1}, zero fill outside
+static bool conv_make_map(CUtensorMap* m, const float* base, int B, int D, int H, int W, int C) {
+    ConvEncodeFn enc = conv_get_encode();
+    if (!enc || !base) return false;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+    cuuint32_t box[5] = {4, (cuuint32_t)HXS, (cuuint32_t)HYS, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // zero_out: y must be all zeros on entry when the launch splits the channel chunks (atomic epilogue); returned through
@@ -393,7 +454,19 @@ static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, c
     g.ksplit = (nchunks + g.cps - 1) / g.cps;
     int tcols = 32;
     while (tcols < Dz * NT) tcols <<= 1;
-    const size_t smem = RING * PLANE_BYTES + 2 * (27 * KJ * NT * 16) + 256;
+    const size_t smem = RING * PLANE_BYTES + 2 * (27 * KJ * NT * 16) + 256 + RING * 8;
+    // TMA planes: channels-last inputs whose channel counts are multiples of 8 (a 4-channel group never straddles x0 | x1
+    // and no K padding is needed); MICFORMER_CONV_TMA=0 keeps the cp.async producers
+    static const bool tma_on = []() { const char* v = getenv("MICFORMER_CONV_TMA"); return !(v && v[0] == '0'); }();
+    CUtensorMap m0, m1;
+    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1));
+    g.use_tma = 0;
+    if (tma_on && !g.in_ncdhw && (g.C0 % 8) == 0 && (g.C1 % 8) == 0) {
+        bool ok = conv_make_map(&m0, x0, g.B, g.D, g.H, g.W, g.C0);
+        if (ok && g.C1 > 0) ok = conv_make_map(&m1, x1, g.B, g.D, g.H, g.W, g.C1);
+        else if (ok) m1 = m0;
+        g.use_tma = ok ? 1 : 0;
+    }
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(conv3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -407,7 +480,7 @@ static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, c
         if (e != cudaSuccess) return fail(MIC_ERR_CUDA, "%s memset: %s", who, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)((int64_t)foot * g.nseg), (unsigned)nych, (unsigned)g.ksplit);
-    mic::launch((conv3_tc_kernel<NT>), grid, dim3(CT_THREADS), smem, st, x0, x1, Wsrc, bias, y0, y1, g, tcols);
+    mic::launch((conv3_tc_kernel<NT>), grid, dim3(CT_THREADS), smem, st, m0, m1, x0, x1, Wsrc, bias, y0, y1, g, tcols);
     return check_launch(who);
 }
 
