@@ -19,12 +19,14 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc5.cuh"
 
 namespace mic {
 
 constexpr int TM = 128;          // output rows per CTA (UMMA M)
 constexpr int TKB = 32;          // reduction elements per stage (128 B of fp32)
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;           // ring depth with the 3xTF32 lo tiles (12 slots of 16 KB)
+constexpr int MAXST = 6;            // single-pass kernels on a grid of at most one CTA per SM: the same 12 slots = 6 stages
 constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (+ converters), warps 6-9 converters
 constexpr int NCONV = 256;             // converter threads (warps 2..9)
 
@@ -43,7 +45,13 @@ struct TcEpi {
                                             // (the tensor core itself truncates; truncation is biased toward zero)
     int split3;                             // 1: 3xTF32 -- x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi);
                                             // D = Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32-faithful, ~2^-21).  Implies round_rn
+                                            // 2: split-bf16 (K-major operands, one-shot kernel): the landed fp32 tile
+                                            // [rows][32 k] is rewritten IN PLACE as [rows][32 k hi | 32 k lo] bf16 and the
+                                            // same three products run as kind::f16 MMAs (K = 16): 6 instead of 12 MMAs per
+                                            // 32-wide k-block (these kernels are MMA-issue bound), ~2^-17, no lo slots
     int nst;                                // pipeline stages in use (3, or 2 when split3 doubles the tiles)
+    float* db;                              // weight-gradient GEMMs (A = dY^T, MN-major): db[i] += sum_r A(i, r), folded into the
+                                            // operand pass of the CTAs with blockIdx.y == 0 (one-shot kernel only)
 };
 
 // optional per-CTA phase trace (debug): 16 x u64 globaltimer stamps per CTA when a buffer is registered
@@ -131,6 +139,36 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// Bias gradient folded into a weight-gradient GEMM (the 256 converter threads, A = dY^T MN-major): thread et holds, per group
+// g of 32 output features, the running sum of float4 (row r = et / 8, chunk c = et % 8) of every A tile of this CTA.  The
+// tile is 128B-swizzled with 32-byte atoms (Swizzle<2,5,2>: address bits 5..6 ^= bits 7..8), so chunk c of row r holds
+// features 8 * ((c >> 1) ^ (r & 3)) + 4 * (c & 1) ... + 3 of the group: the four lanes {r & 3 = 0..3} that hold the same
+// features are lane ^ 10 and lane ^ 20 apart (butterfly), the eight warps meet in shared memory (no shared-memory float
+// atomics: those are CAS loops), then one global atomicAdd per feature, scaled by the split's DropPath factor like dW.
+__device__ __forceinline__ void colsum_flush(float4 (&acc)[4], float* sred, int et, int i0, const TcEpi& e, int kb0) {
+    const int lane = et & 31, w = et >> 5;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int m = 10; m <= 20; m += 10) {
+            acc[g].x += __shfl_xor_sync(0xffffffffu, acc[g].x, m);
+            acc[g].y += __shfl_xor_sync(0xffffffffu, acc[g].y, m);
+            acc[g].z += __shfl_xor_sync(0xffffffffu, acc[g].z, m);
+            acc[g].w += __shfl_xor_sync(0xffffffffu, acc[g].w, m);
+        }
+        if (lane < 8) *reinterpret_cast<float4*>(sred + w * TM + g * 32 + 4 * lane) = acc[g];     // r & 3 == 0: features 4c..4c+3
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (et < TM && i0 + et < e.I) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCONV / 32; ++k) v += sred[k * TM + et];
+        const float rs = e.rowscale_r ? e.rowscale_r[(int64_t)kb0 * TKB / e.rps_r] : 1.f;
+        v *= rs;
+        if (v != 0.f) atomicAdd(e.db + i0 + et, v);
+    }
+}
+
 // BNT: B-tile columns (UMMA N, multiple of 16, <= 128); TCOLS: TMEM columns (power of two >= BNT)
 // EPI (compile-time epilogue kind, keeps the drain loop small and branch-free):
 //   0 plain store (+bias, *rowscale)   1 bias + save pre-activation + erf-GELU   2 residual: res + rowscale*(acc+bias)
@@ -148,25 +186,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int B_STRIDE = 128 * TKB * 4;                       // fixed slot size (16 KB) keeps every slot 1024-aligned
     const int NST = e.nst;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
+    const int NSLOT = e.split3 == 1 ? 4 * STAGES : 2 * NST;   // 16 KB slots in the ring
+    uint8_t* sB = smem + (e.split3 == 1 ? STAGES : NST) * A_BYTES;
     // split3 keeps the "lo" tiles in a second set of slots:  [A0 A1 A2 | B0 B1 B2 | Alo0..2 | Blo0..2]  (16 KB each)
     uint8_t* sAlo = smem + 2 * STAGES * A_BYTES;
     uint8_t* sBlo = sAlo + STAGES * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (e.split3 ? 12 : 6) * A_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSLOT * A_BYTES);
+    uint64_t* empty = full + MAXST;
+    uint64_t* tmem_full = empty + MAXST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    uint64_t* conv = tmem_full + 2;          // [STAGES] operands rounded (arrived by the 4 converter warps)
+    uint64_t* conv = tmem_full + 2;          // [MAXST] operands rounded (arrived by the 8 converter warps)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * TM, j0 = blockIdx.y * BNT;
     const int kb0 = blockIdx.z * e.kb_per_split;
     const int kb1 = min(e.kb_total, kb0 + e.kb_per_split);
     const int nkb = kb1 - kb0;
+    // bias gradient of a weight-gradient GEMM: the converter warps add up the rows of the dY^T tiles as they pass
+    const bool do_sum = A_MN && B_MN && EPI == 5 && e.db != nullptr && blockIdx.y == 0;
+    float* sdb = reinterpret_cast<float*>(smem + NSLOT * A_BYTES + 256 + 512);     // [8 warps][128] partial sums (4 KB)
 
     if (threadIdx.x == 0) trace(0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], NCONV / 32); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], NCONV / 32); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -217,18 +259,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NST;
                 const uint32_t ph = (kb / NST) & 1;
-                mbar_wait(e.round_rn ? &conv[s] : &full[s], ph);
+                mbar_wait((e.round_rn || do_sum) ? &conv[s] : &full[s], ph);
                 tc_fence_after();
                 if (kb == 0) trace(4);
                 const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
                 const uint32_t b_addr = smem_u32(sB + s * B_STRIDE);
+                if (!A_MN && !B_MN && e.split3 == 2) {
+                    // rows are [32 k hi | 32 k lo] bf16: hi k-step ks at +32 ks bytes, lo at +64 + 32 ks
+                    const uint32_t id16 = t5::idesc_bf16(TM, BNT, false, false);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        t5::mma3(tmem_base, make_desc(a_addr + ks * 32, 16, 1024, 2), make_desc(a_addr + 64 + ks * 32, 16, 1024, 2),
+                                 make_desc(b_addr + ks * 32, 16, 1024, 2), make_desc(b_addr + 64 + ks * 32, 16, 1024, 2), id16,
+                                 (kb | ks) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < TKB / 8; ++k) {
                     // MN-major: [group][32 r][128 B]; atom = 4 r-rows (512 B): LBO = group stride, SBO = 512 B, 8 r per MMA
                     const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
                     const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                    if (e.split3) {
+                    if (e.split3 == 1) {
                         const uint32_t al = smem_u32(sAlo + s * A_BYTES), bl = smem_u32(sBlo + s * B_STRIDE);
                         const uint64_t adl = A_MN ? make_desc(al + k * 1024, 4096, 512, 1) : make_desc(al + k * 32, 16, 1024, 2);
                         const uint64_t bdl = B_MN ? make_desc(bl + k * 1024, 4096, 512, 1) : make_desc(bl + k * 32, 16, 1024, 2);
@@ -245,17 +298,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ---------------- epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = output rows i0 + 32q + lane
         const int q = warp & 3;
         const int gi = i0 + q * 32 + lane;
+        if (!e.round_rn && do_sum) {
+            // single-pass TF32 (operands used as they landed): the converter warps only add up dY^T.  A tile = 4 groups of
+            // [32 r][32 i] floats; float4 (et + 256 g) is row r = et / 8, 16-byte chunk c = et % 8 of group g
+            const int et = (warp - 2) * 32 + lane;
+            float4 acc[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NST;
+                const uint32_t ph = (kb / NST) & 1;
+                mbar_wait(&full[s], ph);
+                const float4* a4 = reinterpret_cast<const float4*>(sA + s * A_BYTES);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 t = a4[et + g * NCONV];
+                    acc[g].x += t.x; acc[g].y += t.y; acc[g].z += t.z; acc[g].w += t.w;
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
+            }
+            colsum_flush(acc, sdb, et, i0, e, kb0);
+        }
         if (e.round_rn) {
             // converter role during the main loop: round the freshly landed A/B tiles to nearest-even TF32 in
             // place (element-wise, so the swizzle is irrelevant), then hand the stage to the MMA warp
             const int et = (warp - 2) * 32 + lane;                       // 0..NCONV-1
             const int b_vec = B_BYTES / 16;
+            float4 acc[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NST;
                 const uint32_t ph = (kb / NST) & 1;
                 mbar_wait(&full[s], ph);
                 float4* a4 = reinterpret_cast<float4*>(sA + s * A_BYTES);
                 float4* b4 = reinterpret_cast<float4*>(sB + s * B_STRIDE);
+                if (!A_MN && !B_MN && e.split3 == 2) {
+                    // in place, row by row: the 4 threads of a row (adjacent lanes) each read two fp32 chunks (8 k), all
+                    // reads of the row complete (__syncwarp), then each writes one hi chunk and one lo chunk
+                    auto rewrite = [&](uint8_t* tile, int item) {
+                        const int r = item >> 2, j = item & 3, x = r & 7;
+                        uint8_t* row = tile + r * 128;
+                        const float4 v0 = *reinterpret_cast<const float4*>(row + (((2 * j) ^ x) << 4));
+                        const float4 v1 = *reinterpret_cast<const float4*>(row + (((2 * j + 1) ^ x) << 4));
+                        uint4 h, l;
+                        t5::split2(v0.x, v0.y, h.x, l.x); t5::split2(v0.z, v0.w, h.y, l.y);
+                        t5::split2(v1.x, v1.y, h.z, l.z); t5::split2(v1.z, v1.w, h.w, l.w);
+                        __syncwarp();
+                        *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) = h;
+                        *reinterpret_cast<uint4*>(row + (((4 + j) ^ x) << 4)) = l;
+                    };
+                    rewrite(sA + s * A_BYTES, et);
+                    rewrite(sA + s * A_BYTES, et + NCONV);
+                    for (int item = et; item < BNT * 4; item += NCONV) rewrite(sB + s * B_STRIDE, item);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
+                    continue;
+                }
                 if (e.split3) {
                     float4* al4 = reinterpret_cast<float4*>(sAlo + s * A_BYTES);
                     float4* bl4 = reinterpret_cast<float4*>(sBlo + s * B_STRIDE);
@@ -281,9 +382,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
                     continue;
                 }
-#pragma unroll 4
-                for (int i = et; i < A_BYTES / 16; i += NCONV) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int i = et + g * NCONV;
                     float4 t = a4[i];
+                    if (do_sum) { acc[g].x += t.x; acc[g].y += t.y; acc[g].z += t.z; acc[g].w += t.w; }
                     uint32_t r0, r1, r2, r3;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(t.x));
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(t.y));
@@ -304,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
             }
+            if (do_sum) colsum_flush(acc, sdb, et, i0, e, kb0);
         }
         if (warp >= 6) goto teardown;           // converter-only warps
         // Drain: TMEM -> registers -> fused epilogue math -> 128B-swizzled staging tile in shared memory (the operand
@@ -315,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float rs = e.rowscale_r ? e.rowscale_r[(int64_t)kb0 * TKB / e.rps_r] : 1.f;
         if (row_ok && e.rowscale_i) rs *= e.rowscale_i[gi / e.rps_i];
         const bool use_bias = e.bias != nullptr && blockIdx.z == 0;
-        float* sbias = reinterpret_cast<float*>(smem + (e.split3 ? 12 : 6) * A_BYTES + 256);
+        float* sbias = reinterpret_cast<float*>(smem + NSLOT * A_BYTES + 256);
         if (use_bias) {
             const int tt = (warp - 2) * 32 + lane;               // 0..127 >= BNT columns of this tile
             if (tt < BNT) sbias[tt] = j0 + tt < e.J ? e.bias[j0 + tt] : 0.f;
@@ -757,7 +861,8 @@ struct TcOperand {
 static bool operand_ok(const TcOperand& o) { return (reinterpret_cast<uintptr_t>(o.p) & 15) == 0 && o.ld % 4 == 0 && o.ld > 0; }
 
 // generic launcher: C[I,J] = sum_R A(i,r) B(r,j)
-static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int kb_per_split, cudaStream_t st) {
+static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int kb_per_split, cudaStream_t st,
+                   bool* db_done = nullptr) {
     if (!operand_ok(A) || !operand_ok(B)) return MIC_ERR_UNSUPPORTED;
     const int I = e.I, J = e.J;
     int BNT = J <= 128 ? ((J + 15) / 16) * 16 : 128;
@@ -794,13 +899,22 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
     e.kb_total = (R + TKB - 1) / TKB;
     e.kb_per_split = (kb_per_split > 0 && kb_per_split < e.kb_total) ? kb_per_split : e.kb_total;
     const int splits = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
-    const size_t smem = 1024 + (size_t)(e.split3 ? 12 : 6) * (TM * TKB * 4) + 256 + 512;   // ring + barriers + bias tile
     dim3 grid((I + TM - 1) / TM, (J + BNT - 1) / BNT, splits);
+    // small grids (the deep, latency-bound stages) never share an SM: single-pass kernels then run a 6-stage ring in the shared
+    // memory the 3xTF32 variant needs anyway, which halves the exposed TMA round trips of a long reduction
+    static const bool deep_ring = []() { const char* v = getenv("MICFORMER_GEMM_DEEP_RING"); return !(v && v[0] == '0'); }();
+    if (e.split3 == 2 && (A.mn_major || B.mn_major)) e.split3 = 1;
+    if (deep_ring && e.split3 != 1 && e.kb_per_split > STAGES && (int64_t)grid.x * grid.y * grid.z <= (int64_t)num_sms()) e.nst = MAXST;
+    const size_t smem = 1024 + (size_t)(e.split3 == 1 ? 12 : 2 * e.nst) * (TM * TKB * 4) + 256 + 512 +
+                        (e.db ? 4096 : 0);                                     // ring + barriers + bias tile (+ db partial sums)
     // several tiles per SM: persistent kernel (epilogue of tile n overlaps the main loop of tile n+1)
     static const bool no_persist = getenv("MICFORMER_GEMM_ONESHOT") != nullptr;
     const int64_t ntiles = (int64_t)grid.x * grid.y * grid.z;
+    if (db_done) *db_done = false;
     if (!no_persist && ntiles >= 2 * (int64_t)num_sms() && ntiles < (1 << 30)) {
         TcpSched sc{};
+        e.db = nullptr;
+        if (e.split3 == 2) e.split3 = 1;
         sc.tiles_i = (int)grid.x; sc.tiles_j = (int)grid.y; sc.splits = splits; sc.ntiles = (int)ntiles;
         sc.stage_slots = e.split3 ? 4 : 2;
         const int stage_bytes = sc.stage_slots * TM * TKB * 4;
@@ -842,7 +956,7 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
         static bool attr_done = false;                                                                           \
         if (!attr_done) {                                                                                        \
             cudaFuncSetAttribute(gemm_tc_kernel<AM, BM_, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                 (int)(1024 + 12 * TM * TKB * 4 + 256 + 512));                                         \
+                                 (int)(1024 + 12 * TM * TKB * 4 + 256 + 512 + 4096));                                  \
             attr_done = true;                                                                                    \
         }                                                                                                        \
         mic::launch((gemm_tc_kernel<AM, BM_, EP>), grid, dim3(TC_THREADS), smem, st, mA, mB, mC, mP, e, BNT, TCOLS);                       \
@@ -856,6 +970,8 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
         case 4: LAUNCH(AM, BM_, 4); break;                                             \
         default: LAUNCH(AM, BM_, 5); break;                                            \
     }
+    if (!(A.mn_major && B.mn_major && epi == 5)) e.db = nullptr;
+    if (db_done) *db_done = e.db != nullptr;
     if (!A.mn_major && !B.mn_major) { LAUNCH_EPI(false, false) }
     else if (!A.mn_major && B.mn_major) { LAUNCH_EPI(false, true) }
     else if (A.mn_major && B.mn_major) { LAUNCH(true, true, 5); }
@@ -889,10 +1005,33 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
     // MICFORMER_TF32_FWD_SMALL_M=<rows>: GEMMs with at most that many rows (the deep, latency-bound stages) run
     // single-pass nearest-rounded TF32; the large-M stages and the decoder tail keep the 3xTF32 split
     static const int small_m = []() { const char* v = getenv("MICFORMER_TF32_FWD_SMALL_M"); return v ? atoi(v) : 0; }();
+    // MICFORMER_FWD_BF16X3=0: 3xTF32 for every forward GEMM (the round-1 path); default: split-bf16 where both operands are K-major
+    static const int bf3 = []() { const char* v = getenv("MICFORMER_FWD_BF16X3"); return !(v && v[0] == '0'); }();
     e.round_rn = 1;
-    e.split3 = (fwd_single || M <= small_m) ? 0 : 1;
+    e.split3 = (fwd_single || M <= small_m) ? 0 : (bf3 && !w_is_kn ? 2 : 1);
     TcOperand A{X, false, ldx};
     TcOperand B{W, w_is_kn != 0, ldw};      // W[n,k]: K-major; W[k,n]: MN-major
+    // Long reductions on a grid that leaves most SMs idle (fc2 of the deep stages: 16 CTAs x 24..48 k-blocks, each k-block paced
+    // by the CTA's shared-memory bandwidth): split the reduction over blockIdx.z.  The output is initialised with the residual
+    // (or zero) by a copy node and every split adds rowscale * (partial [+ bias in split 0]) with TMA reduce-add.
+    static const bool splitk = []() { const char* v = getenv("MICFORMER_FWD_SPLITK"); return !(v && v[0] == '0'); }();
+    if (splitk && !act && !accumulate && !pre && M > 0) {
+        const int kb_total = (K + TKB - 1) / TKB;
+        int bnt = N <= 128 ? ((N + 15) / 16) * 16 : 128;
+        if (N > 128) { const int nt = (N + 127) / 128; bnt = (((N + nt - 1) / nt) + 31) / 32 * 32; }
+        const int tiles = ((M + TM - 1) / TM) * ((N + bnt - 1) / bnt);
+        int smax = kb_total / 4;
+        if (smax > num_sms() / tiles) smax = num_sms() / tiles;
+        if (smax > 8) smax = 8;
+        if (kb_total >= 12 && smax >= 2) {
+            cudaError_t ce = cudaSuccess;
+            if (res && res != Y) ce = cudaMemcpy2DAsync(Y, (size_t)ldy * 4, res, (size_t)ldres * 4, (size_t)N * 4, (size_t)M, cudaMemcpyDeviceToDevice, st);
+            else if (!res) ce = cudaMemset2DAsync(Y, (size_t)ldy * 4, 0, (size_t)N * 4, (size_t)M, st);
+            if (ce != cudaSuccess) return MIC_ERR_CUDA;
+            e.res = nullptr; e.accumulate = 2;
+            return tc_gemm(A, B, e, K, (kb_total + smax - 1) / smax, st);
+        }
+    }
     return tc_gemm(A, B, e, K, 0, st);
 }
 
@@ -934,9 +1073,13 @@ int tc_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, flo
         while (kb_rps % kb_per) --kb_per;
         e.rowscale_r = rowscale; e.rps_r = rps;
     }
-    int rc = tc_gemm(A, B, e, M, kb_per, st);
+    // the bias gradient rides along when dY is the A operand (its tiles pass the converter warps of the blockIdx.y == 0 CTAs)
+    static const bool fold = []() { const char* v = getenv("MICFORMER_FOLD_COLSUM"); return !(v && v[0] == '0'); }();
+    if (db && !w_is_kn && fold) e.db = db;
+    bool db_done = false;
+    int rc = tc_gemm(A, B, e, M, kb_per, st, &db_done);
     if (rc) return rc;
-    if (db) return colsum(dY, lddy, M, N, rowscale, rps > 0 ? rps : 1, db, st);
+    if (db && !db_done) return colsum(dY, lddy, M, N, rowscale, rps > 0 ? rps : 1, db, st);
     return MIC_OK;
 }
 

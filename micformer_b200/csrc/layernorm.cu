@@ -139,15 +139,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         int64_t row = 0;
         const bool live = prow < prows && padded_to_row(g, prow, row);
         const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
-        float4 xh[VPL], gg[VPL];
+        float4 xh[VPL], gg[VPL], rr[VPL];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int c = 4 * (gl + lpr * i);
-            xh[i] = make_float4(0.f, 0.f, 0.f, 0.f); gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            xh[i] = make_float4(0.f, 0.f, 0.f, 0.f); gg[i] = make_float4(0.f, 0.f, 0.f, 0.f); rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && c < C) {
                 const float4 d = __ldg(reinterpret_cast<const float4*>(dy + prow * C + c));
                 const float4 xv = ld_cat4v(x0, C0, x1, C1, row, c);
+                // the residual gradient is only needed after the row reductions: fetch it with the other operands
+                const float* dres = c < C0 ? dres0 : dres1;
+                if (dres) rr[i] = __ldg(reinterpret_cast<const float4*>(c < C0 ? dres + row * C0 + c : dres + row * C1 + (c - C0)));
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 gg[i] = make_float4(d.x * gam[i].x, d.y * gam[i].y, d.z * gam[i].z, d.w * gam[i].w);
                 pg[i].x += d.x * xh[i].x; pg[i].y += d.y * xh[i].y; pg[i].z += d.z * xh[i].z; pg[i].w += d.w * xh[i].w;
@@ -165,17 +168,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
             if (c < C) {
                 float4 v = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2), rs * (gg[i].y - s1 - xh[i].y * s2),
                                        rs * (gg[i].z - s1 - xh[i].z * s2), rs * (gg[i].w - s1 - xh[i].w * s2));
-                const float* dres = c < C0 ? dres0 : dres1;
                 float* dx = c < C0 ? dx0 + row * C0 + c : dx1 + row * C1 + (c - C0);
-                if (dres) {
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(c < C0 ? dres + row * C0 + c : dres + row * C1 + (c - C0)));
-                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-                }
+                v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
                 *reinterpret_cast<float4*>(dx) = v;
             }
         }
     }
-    // fold the lane groups of the warp (same channels), then warps through shared memory
+    // fold the lane groups of the warp (same channels) by shuffles, then the warps take turns adding their partial sums to the
+    // shared accumulators (float atomicAdd on shared memory is a compare-and-swap loop: 8 contending warps cost microseconds)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         for (int o = lpr; o < 32; o <<= 1) {
@@ -184,14 +184,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
             pb[i].x += __shfl_xor_sync(0xffffffffu, pb[i].x, o); pb[i].y += __shfl_xor_sync(0xffffffffu, pb[i].y, o);
             pb[i].z += __shfl_xor_sync(0xffffffffu, pb[i].z, o); pb[i].w += __shfl_xor_sync(0xffffffffu, pb[i].w, o);
         }
-        const int c = 4 * (gl + lpr * i);
-        if (gi == 0 && c < C) {
-            atomicAdd(&red[c], pg[i].x); atomicAdd(&red[c + 1], pg[i].y); atomicAdd(&red[c + 2], pg[i].z); atomicAdd(&red[c + 3], pg[i].w);
-            atomicAdd(&red[C + c], pb[i].x); atomicAdd(&red[C + c + 1], pb[i].y); atomicAdd(&red[C + c + 2], pb[i].z);
-            atomicAdd(&red[C + c + 3], pb[i].w);
-        }
     }
-    __syncthreads();
+    for (int w = 0; w < nw; ++w) {
+        if (wid == w && gi == 0) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c = 4 * (gl + lpr * i);
+                if (c < C) {
+                    float4* rg = reinterpret_cast<float4*>(red + c);
+                    float4* rb = reinterpret_cast<float4*>(red + C + c);
+                    float4 a = *rg, b = *rb;
+                    a.x += pg[i].x; a.y += pg[i].y; a.z += pg[i].z; a.w += pg[i].w;
+                    b.x += pb[i].x; b.y += pb[i].y; b.z += pb[i].z; b.w += pb[i].w;
+                    *rg = a; *rb = b;
+                }
+            }
+        }
+        __syncthreads();
+    }
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         atomicAdd(&dgamma[c], red[c]);
         atomicAdd(&dbeta[c], red[C + c]);

@@ -4,7 +4,7 @@ import torch
 from micformer_b200 import ops, _native as N
 lib = N.load(); lib.mic_debug_tc_trace.argtypes = [ctypes.c_void_p]
 dev = "cuda"; N.set_gemm_mode(1)
-for (M, Nn, K) in [(65536, 192, 48), (1024, 192, 192), (1024, 192, 768), (128, 384, 1536), (65536, 48, 48)]:
+for (M, Nn, K) in [(1024, 192, 192), (1024, 192, 768), (1024, 768, 192), (8192, 96, 384), (128, 384, 1536)]:
     x = torch.randn(M, K, device=dev); w = torch.randn(Nn, K, device=dev); b = torch.randn(Nn, device=dev)
     for _ in range(3): ops.linear_fwd(x, K, w, b, M, Nn, K)
     buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
