@@ -113,9 +113,15 @@ int mic_conv3_tc_fwd(const float* x0, int C0, const float* x1, int C1, const flo
 int mic_conv3_tc_bwd_data(const float* dy, const float* Wt, float* dx0, int C0, int acc0, float* dx1, int C1, int acc1,
                           int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream);
 /* Tensor-core backward-weight (warp-level mma.sync m16n8k8 TF32; the reduction runs over positions, so the 27 taps
- * are index-shifted shared-memory fragment loads): same result as mic_conv3_bwd_weight on an unpadded grid, Co in {8,16}. */
+ * are index-shifted shared-memory fragment loads): same result as mic_conv3_bwd_weight on an unpadded grid, Co in {8,16}.
+ * native_layout != 0: dWt is the nn.Conv3d parameter's own (Co, Cin, 3, 3, 3) gradient (accumulated in place) instead
+ * of the permuted [27][Cin][Co] buffer. */
 int mic_conv3_mma_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
-                             int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream);
+                             int B, int D, int H, int W, int Co, int dy_ncdhw, int native_layout, void* stream);
+/* The two operand layouts the conv kernels read, [27][Cin][Co] and [27][Co][Cin], of n_jobs nn.Conv3d(k=3) weights
+ * (Co, Cin, 3, 3, 3) in ONE launch (once per model forward, like mic_weight_images).  jobs: device array of n_jobs x 5
+ * int64 {src, dst_tap_ci_co, dst_tap_co_ci, Cin, Co}; max_elems = largest 27*Cin over the jobs, max_co = largest Co (<= 64). */
+int mic_conv_weight_layouts(const void* jobs, int n_jobs, int64_t max_elems, int max_co, void* stream);
 
 /* ---- Offset head: LayerNormProxy(16) -> GELU -> Conv3d(16->3,k1,no bias) -> + reference points
  *      (:315-317, :326-337, :360-364).  h (P,HC) -> pos (P,3) with P = B*Dp*Hp*Wp. */

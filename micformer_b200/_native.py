@@ -35,7 +35,7 @@ SIGNATURES = {
     "mic_conv3_bwd_data": [P, P, P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "mic_conv3_tc_bwd_data": [P, P, P, I, I, P, I, I, I, I, I, I, I, I, P],
     "mic_conv3_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
-    "mic_conv3_mma_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, P],
+    "mic_conv3_mma_bwd_weight": [P, P, I, P, I, P, P, I, I, I, I, I, I, I, P],
     "mic_offset_head_fwd": [P, P, P, P, P, I, I, I, I, I, F, P],
     "mic_offset_head_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, P],
     "mic_deform_sample_fwd": [P, P, P, I, I, I, I, I, I, I, I, P],
@@ -50,6 +50,7 @@ SIGNATURES = {
     "mic_adam_chunk_elems": [],
     "mic_adam_step": [P, P, P, P, P, P, P, I, I, P, P, F, F, F, F, P],
     "mic_weight_images": [P, I, L, P],
+    "mic_conv_weight_layouts": [P, I, L, I, P],
     "mic_mlp_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, F, P],
     "mic_mlp_block_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, F, P],
     "mic_mlp_block_smem": [I],

@@ -49,6 +49,40 @@ __global__ void __launch_bounds__(256) weight_image_kernel(const ImgJob* __restr
     }
 }
 
+// The conv kernels' operand layouts of many Conv3d(k=3) weights in one launch: src (Co, Cin, 27) -> [27][Cin][Co], [27][Co][Cin]
+struct ConvWJob {
+    const float* src; float* tcio; float* toci; int64_t Cin, Co;
+};
+static_assert(sizeof(ConvWJob) == 5 * 8, "ConvWJob is passed as 5 x int64 from the host side");
+
+// CTA = (job, 32-input-channel chunk): the chunk's [Co][32][27] block goes through shared memory so that the reads and both
+// writes are contiguous runs (27-float rows in, 32 x Co / 32-float runs out)
+__global__ void __launch_bounds__(256) conv_weight_layout_kernel(const ConvWJob* __restrict__ jobs) {
+    pdl_sync();
+    const ConvWJob j = jobs[blockIdx.y];
+    const int Cin = (int)j.Cin, Co = (int)j.Co;
+    const int c0 = blockIdx.x * 32;
+    if (c0 >= Cin) return;
+    const int nc = min(32, Cin - c0);
+    extern __shared__ float cwl[];                 // [Co][nc * 27 (+1 pad)]
+    const int row = nc * 27, rowp = row + 1;
+    for (int i = threadIdx.x; i < Co * row; i += blockDim.x) {
+        const int co = i / row, r = i - co * row;
+        cwl[co * rowp + r] = j.src[((int64_t)co * Cin + c0) * 27 + r];
+    }
+    __syncthreads();
+    // tcio[tap][ci][co]: per tap a run of nc * Co floats
+    for (int i = threadIdx.x; i < 27 * nc * Co; i += blockDim.x) {
+        const int co = i % Co, ci = (i / Co) % nc, tap = i / (Co * nc);
+        j.tcio[((int64_t)tap * Cin + c0 + ci) * Co + co] = cwl[co * rowp + ci * 27 + tap];
+    }
+    // toci[tap][co][ci]: per (tap, co) a run of nc floats
+    for (int i = threadIdx.x; i < 27 * Co * nc; i += blockDim.x) {
+        const int ci = i % nc, co = (i / nc) % Co, tap = i / (nc * Co);
+        j.toci[((int64_t)tap * Co + co) * Cin + c0 + ci] = cwl[co * rowp + ci * 27 + tap];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 struct MlpFwdArgs {
     const float* x; float* y;
@@ -290,6 +324,19 @@ extern "C" int mic_weight_images(const void* jobs, int n_jobs, int64_t max_chunk
     if (gx > 64) gx = 64;
     mic::launch(weight_image_kernel, dim3(gx, n_jobs), dim3(256), 0, (cudaStream_t)stream, (const ImgJob*)jobs);
     return check_launch("weight_image_kernel");
+}
+
+extern "C" int mic_conv_weight_layouts(const void* jobs, int n_jobs, int64_t max_elems, int max_co, void* stream) {
+    MIC_REQUIRE(jobs && n_jobs > 0 && max_elems > 0 && max_co > 0 && max_co <= 64, "conv_weight_layouts: bad arguments");
+    const int max_cin = (int)(max_elems / 27);                 // an upper bound of every job's Cin (Co >= 1)
+    const size_t smem = (size_t)max_co * (32 * 27 + 1) * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && attr < smem) {
+        cudaFuncSetAttribute(conv_weight_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    mic::launch(conv_weight_layout_kernel, dim3((max_cin + 31) / 32, n_jobs), dim3(256), smem, (cudaStream_t)stream, (const ConvWJob*)jobs);
+    return check_launch("conv_weight_layout_kernel");
 }
 
 extern "C" int mic_mlp_block_smem(int C) {

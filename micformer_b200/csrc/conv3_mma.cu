@@ -47,7 +47,7 @@ template <int COP>   // 8 or 16 output channels (padded)
 __global__ void __launch_bounds__(M_THREADS, 2)
 conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x0, const float* __restrict__ x1,
                             float* __restrict__ dWt, float* __restrict__ dbias, MGeom g, int dy_ncdhw, int nbz, int nby,
-                            int nbx) {
+                            int nbx, int native) {
     pdl_sync();
     constexpr int NTN = COP / 8;
     extern __shared__ __align__(16) float msm[];
@@ -73,6 +73,10 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
 #pragma unroll
                 for (int d = 0; d < 4; ++d) acc[a][b][c][d] = 0.f;
     if (tid < 16) bsum[tid] = 0.f;
+    constexpr int DLB = (M_NB * COP + M_THREADS - 1) / M_THREADS;
+    float bacc[DLB];
+#pragma unroll
+    for (int i = 0; i < DLB; ++i) bacc[i] = 0.f;
 
     for (int64_t brick = blockIdx.x; brick < nbricks; brick += gridDim.x) {
         int64_t t = brick;
@@ -133,18 +137,7 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
                 int pos, o;
                 if (dy_ncdhw) { pos = idx % M_NB; o = idx / M_NB; } else { o = idx % COP; pos = idx / COP; }
                 dYs[pos * DS + o] = to_tf32(dv[i]);
-                if (want_bias) {
-                    // lanes of a warp share o (NCDHW: 128 % 32 == 0) or hold o = lane % COP (channels-last)
-                    float s = dv[i];
-                    if (dy_ncdhw) {
-                        s = warp_sum(s);
-                        if (lane == 0 && o < g.Co) atomicAdd(&bsum[o], s);
-                    } else {
-#pragma unroll
-                        for (int off = 16; off >= COP; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                        if (lane < COP && o < g.Co) atomicAdd(&bsum[o], s);
-                    }
-                }
+                if (want_bias) bacc[i] += dv[i];          // (pos, o) of slot i is the same for every brick: reduce once at the end
             }
         }
         __syncthreads();
@@ -182,21 +175,66 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
         }
     }
     // flush: c0:(row gq, col 2 tq) c1:(gq, 2tq+1) c2:(gq+8, 2tq) c3:(gq+8, 2tq+1); row = ci within the m-tile, col = co
+    if (native) {
+        // the Conv3d parameter's own layout [co][ci][tap]: stage the CTA's [COP][32 ci][27] block in shared memory (the x halo is
+        // dead) so that the global atomics run over contiguous (ci, tap) spans instead of 27-float strides
+        __syncthreads();
 #pragma unroll
-    for (int tx = 0; tx < 3; ++tx) {
-        const int tap = (tz * 3 + ty) * 3 + tx;
+        for (int tx = 0; tx < 3; ++tx) {
+            const int tap = (tz * 3 + ty) * 3 + tx;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < NTN; ++nt)
+                for (int nt = 0; nt < NTN; ++nt)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int ci = c0 + mt * 16 + gq + (r >> 1) * 8;
-                    const int co = nt * 8 + 2 * tq + (r & 1);
-                    if (ci < Cin && co < g.Co) atomicAdd(&dWt[((int64_t)tap * Cin + ci) * g.Co + co], acc[tx][mt][nt][r]);
-                }
+                    for (int r = 0; r < 4; ++r) {
+                        const int cl = mt * 16 + gq + (r >> 1) * 8;
+                        const int co = nt * 8 + 2 * tq + (r & 1);
+                        Xs[(co * 32 + cl) * 27 + tap] = acc[tx][mt][nt][r];
+                    }
+        }
+        __syncthreads();
+        const int nci = min(32, Cin - c0);
+        for (int idx = tid; idx < COP * 32 * 27; idx += M_THREADS) {
+            const int co = idx / (32 * 27), rem = idx - co * (32 * 27);
+            if (co < g.Co && rem < nci * 27) {
+                const float v = Xs[idx];
+                if (v != 0.f) atomicAdd(&dWt[((int64_t)co * Cin + c0) * 27 + rem], v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+            const int tap = (tz * 3 + ty) * 3 + tx;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTN; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int ci = c0 + mt * 16 + gq + (r >> 1) * 8;
+                        const int co = nt * 8 + 2 * tq + (r & 1);
+                        if (ci < Cin && co < g.Co) atomicAdd(&dWt[((int64_t)tap * Cin + ci) * g.Co + co], acc[tx][mt][nt][r]);
+                    }
+        }
     }
     if (want_bias) {
+        // lanes of a warp share o (NCDHW: 128 % 32 == 0) or hold o = lane % COP (channels-last)
+#pragma unroll
+        for (int i = 0; i < DLB; ++i) {
+            const int idx = tid + i * M_THREADS;
+            if (idx >= M_NB * COP) continue;
+            const int o = dy_ncdhw ? idx / M_NB : idx % COP;
+            float s = bacc[i];
+            if (dy_ncdhw) {
+                s = warp_sum(s);
+                if (lane == 0 && o < g.Co) atomicAdd(&bsum[o], s);
+            } else {
+#pragma unroll
+                for (int off = 16; off >= COP; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane < COP && o < g.Co) atomicAdd(&bsum[o], s);
+            }
+        }
         __syncthreads();
         if (tid < g.Co) atomicAdd(&dbias[tid], bsum[tid]);
     }
@@ -205,7 +243,7 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
 }  // namespace
 
 int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
-                         int B, int D, int H, int W, int Co, int dy_ncdhw, cudaStream_t st) {
+                         int B, int D, int H, int W, int Co, int dy_ncdhw, int native, cudaStream_t st) {
     if ((Co != 8 && Co != 16) || (C0 & 3) || (C1 & 3)) return MIC_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x0) & 15) || (x1 && (reinterpret_cast<uintptr_t>(x1) & 15))) return MIC_ERR_UNSUPPORTED;
     MGeom g{B, D, H, W, C0, C1, Co};
@@ -223,11 +261,11 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
     if (Co == 8) {
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(conv3_mma_bwd_weight_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-        mic::launch((conv3_mma_bwd_weight_kernel<8>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_mma_bwd_weight_kernel<8>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx, native);
     } else {
         static bool once = false;
         if (!once) { cudaFuncSetAttribute(conv3_mma_bwd_weight_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-        mic::launch((conv3_mma_bwd_weight_kernel<16>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx);
+        mic::launch((conv3_mma_bwd_weight_kernel<16>), grid, dim3(M_THREADS), smem, st, dy, x0, x1, dWt, dbias, g, dy_ncdhw, nbz, nby, nbx, native);
     }
     return check_launch("conv3_mma_bwd_weight_kernel");
 }
@@ -235,9 +273,11 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
 }  // namespace mic
 
 extern "C" int mic_conv3_mma_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt,
-                                        float* dbias, int B, int D, int H, int W, int Co, int dy_ncdhw, void* stream) {
+                                        float* dbias, int B, int D, int H, int W, int Co, int dy_ncdhw, int native_layout,
+                                        void* stream) {
     MIC_REQUIRE(dy && x0 && dWt && (C1 == 0 || x1), "conv3_mma_bwd_weight: null pointer");
-    int rc = mic::mma_conv3_bwd_weight(dy, x0, C0, x1, C1, dWt, dbias, B, D, H, W, Co, dy_ncdhw, (cudaStream_t)stream);
+    int rc = mic::mma_conv3_bwd_weight(dy, x0, C0, x1, C1, dWt, dbias, B, D, H, W, Co, dy_ncdhw, native_layout != 0,
+                                       (cudaStream_t)stream);
     if (rc == MIC_ERR_UNSUPPORTED) return mic::fail(MIC_ERR_UNSUPPORTED, "conv3_mma_bwd_weight: Co=%d / channel split not taken", Co);
     return rc;
 }

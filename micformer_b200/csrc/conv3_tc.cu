@@ -438,7 +438,9 @@ static int launch_conv_tc(const float* x0, const float* x1, const float* Wsrc, c
     const int nych = (Ntot + NT - 1) / NT;
     g.nfy = (g.H + TY - 1) / TY; g.nfx = (g.W + TX - 1) / TX;
     const int foot = g.B * g.nfy * g.nfx;
-    const int target = 2 * num_sms();
+    // CTAs wanted before the z segments stop shrinking / the channel chunks are split (MICFORMER_CONV_TARGET_PCT: % of the SM count)
+    static const int target_pct = []() { const char* v = getenv("MICFORMER_CONV_TARGET_PCT"); return v ? atoi(v) : 200; }();
+    const int target = num_sms() * target_pct / 100;
     // z segment length: enough CTAs to fill the GPU; Dz * NT accumulator columns, 3 (NT=16) or 2 (NT=32) CTAs per SM
     int Dz = 8;
     while (Dz > 2 && (int64_t)foot * ((g.D + Dz - 1) / Dz) * nych < target) Dz >>= 1;

@@ -66,10 +66,9 @@ __global__ void __launch_bounds__(256) offset_head_bwd_kernel(const float* __res
                                                               float* __restrict__ dw3, int64_t P, float eps) {
     pdl_sync();
     __shared__ float sg[HC], sb[HC], sw[3 * HC];
-    __shared__ float red[5 * HC];   // dgamma | dbeta | dw3[3][HC]
+    __shared__ float red[8][5 * HC];   // per warp: dgamma | dbeta | dw3[3][HC]  (no shared-memory float atomics: CAS loops)
     if (threadIdx.x < HC) { sg[threadIdx.x] = gamma[threadIdx.x]; sb[threadIdx.x] = beta[threadIdx.x]; }
     if (threadIdx.x < 3 * HC) sw[threadIdx.x] = w3[threadIdx.x];
-    if (threadIdx.x < 5 * HC) red[threadIdx.x] = 0.f;
     __syncthreads();
     float ag[HC], ab[HC], aw0[HC], aw1[HC], aw2[HC];
 #pragma unroll
@@ -118,22 +117,25 @@ __global__ void __launch_bounds__(256) offset_head_bwd_kernel(const float* __res
             *reinterpret_cast<float4*>(dh + p * HC + c * 4) = t;
         }
     }
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < HC; ++c) {
         const float r0 = warp_sum(ag[c]), r1 = warp_sum(ab[c]), r2 = warp_sum(aw0[c]), r3 = warp_sum(aw1[c]),
                     r4 = warp_sum(aw2[c]);
         if (lane == 0) {
-            atomicAdd(&red[c], r0); atomicAdd(&red[HC + c], r1); atomicAdd(&red[2 * HC + c], r2);
-            atomicAdd(&red[3 * HC + c], r3); atomicAdd(&red[4 * HC + c], r4);
+            red[wid][c] = r0; red[wid][HC + c] = r1; red[wid][2 * HC + c] = r2;
+            red[wid][3 * HC + c] = r3; red[wid][4 * HC + c] = r4;
         }
     }
     __syncthreads();
-    if (threadIdx.x < HC) {
-        atomicAdd(&dgamma[threadIdx.x], red[threadIdx.x]);
-        atomicAdd(&dbeta[threadIdx.x], red[HC + threadIdx.x]);
+    if (threadIdx.x < 5 * HC) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        if (threadIdx.x < HC) atomicAdd(&dgamma[threadIdx.x], v);
+        else if (threadIdx.x < 2 * HC) atomicAdd(&dbeta[threadIdx.x - HC], v);
+        else atomicAdd(&dw3[threadIdx.x - 2 * HC], v);
     }
-    if (threadIdx.x < 3 * HC) atomicAdd(&dw3[threadIdx.x], red[2 * HC + threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------ deformable gather

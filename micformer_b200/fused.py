@@ -104,6 +104,49 @@ def mlp_images(fc1_w: torch.Tensor, fc2_w: torch.Tensor) -> WeightImages:
     ])
 
 
+class ConvLayouts:
+    """The two operand layouts the 3x3x3 conv kernels read -- ``tcio`` (27, Cin, Co) and ``toci`` (27, Co, Cin) -- of one
+    nn.Conv3d(k=3) weight (Co, Cin, 3, 3, 3), kept in persistent buffers and rewritten once per model forward by
+    ``mic_conv_weight_layouts`` (one launch for all convolutions of a model) instead of two permuted copies per block."""
+
+    def __init__(self, weight: torch.Tensor):
+        if not (weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous() and tuple(weight.shape[2:]) == (3, 3, 3)):
+            raise RuntimeError("ConvLayouts: contiguous CUDA float32 (Co, Cin, 3, 3, 3) weight expected")
+        co, cin = weight.shape[:2]
+        self.weight = weight
+        self.tcio = torch.empty(27, cin, co, device=weight.device)
+        self.toci = torch.empty(27, co, cin, device=weight.device)
+        self.elems = 27 * cin            # grid bound: 32-channel chunks of the widest job
+        self.co = co
+        self.job_host = [weight.data_ptr(), self.tcio.data_ptr(), self.toci.data_ptr(), cin, co]
+        self.job = torch.tensor([self.job_host], dtype=torch.int64, device=weight.device)
+        self._ptr = weight.data_ptr()
+        self.stamp = -1
+
+    def valid(self) -> bool:
+        return self.weight.data_ptr() == self._ptr
+
+    def refresh(self) -> None:
+        N.call("mic_conv_weight_layouts", N.ptr(self.job), 1, self.elems, self.co)
+
+
+def refresh_conv_layouts(convs: List["ConvLayouts"]) -> None:
+    if not convs:
+        return
+    key = tuple(id(c) for c in convs)
+    ent = refresh_conv_layouts._cache.get(key)
+    if ent is None:
+        jobs = torch.cat([c.job for c in convs], dim=0).contiguous()
+        ent = refresh_conv_layouts._cache[key] = (jobs, (max(c.elems for c in convs), max(c.co for c in convs)), convs)
+        if len(refresh_conv_layouts._cache) > 8:
+            refresh_conv_layouts._cache.pop(next(iter(refresh_conv_layouts._cache)))
+    jobs, (me, mco), _ = ent
+    N.call("mic_conv_weight_layouts", N.ptr(jobs), jobs.shape[0], me, mco)
+
+
+refresh_conv_layouts._cache = {}
+
+
 _epoch = 0        # bumped by every model-level refresh; an image set whose stamp equals it is current
 
 
@@ -111,18 +154,23 @@ def epoch() -> int:
     return _epoch
 
 
-def model_refresh(images: List[WeightImages]) -> None:
-    """Called once per model forward (the optimizer changed the weights): one launch converts all images."""
+def model_refresh(images: List[WeightImages], convs: Optional[List[ConvLayouts]] = None) -> None:
+    """Called once per model forward (the optimizer changed the weights): one launch converts all images, one more
+    rewrites the operand layouts of all 3x3x3 conv weights."""
     global _epoch
     _epoch += 1
     if images:
         refresh_all(images)
         for i in images:
             i.stamp = _epoch
+    if convs:
+        refresh_conv_layouts(convs)
+        for c in convs:
+            c.stamp = _epoch
 
 
-def ensure_current(img: Optional[WeightImages]) -> None:
-    """A block used stand-alone (no enclosing model refreshed this forward) converts its own images."""
+def ensure_current(img) -> None:
+    """A block used stand-alone (no enclosing model refreshed this forward) converts its own images / layouts."""
     if img is not None and img.stamp != _epoch:
         img.refresh()
 

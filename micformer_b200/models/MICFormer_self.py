@@ -92,6 +92,20 @@ def _attn_images(attn):
     return img
 
 
+# MICFORMER_CONV_LAYOUTS=1: conv_offset weights reach the kernels through persistent layout buffers rewritten once per forward
+# (one launch) and their gradient is written in the parameter's own layout: 144 fewer torch copy kernels per step, but the
+# strided gradient flush costs 5-8 us per cross block on the weight-gradient branch (21.45 vs 21.25 ms/step): off by default
+_CONV_LAYOUTS = _os.environ.get("MICFORMER_CONV_LAYOUTS", "0") == "1"
+
+
+def _conv_layouts(conv):
+    """persistent [27][Cin][Co] / [27][Co][Cin] copies of a Conv3d(k=3) weight for the conv kernels (cached on the module)"""
+    lay = conv.__dict__.get("_mic_lay")
+    if lay is None or not lay.valid():
+        lay = conv.__dict__["_mic_lay"] = fused.ConvLayouts(conv.weight.detach())
+    return lay
+
+
 def _fused_block_images(block, attn, dims):
     """(attention images, MLP images) when BOTH halves of this block run as fused kernels for this geometry, else None"""
     C = block.dim
@@ -312,25 +326,29 @@ class CrossTransformerBlock3D(nn.Module):
         a = self.cross_attn
         co = self.conv_offset
         imgs = _fused_block_images(self, a, x.shape[1:4]) if x.is_cuda else None
-        if imgs is not None:
+        w3 = co[3].weight.reshape(3, self.hidden_channels)
+        if x.is_cuda and co[0].weight.is_contiguous() and _CONV_LAYOUTS:
+            # the conv kernels read layout copies of conv_offset.0.weight that are rewritten once per model forward; the weight's
+            # gradient comes back in the parameter's own layout (cwp)
+            lay = _current(_conv_layouts(co[0]))
+            cw, cwk, cwp = lay.tcio, lay.toci, co[0].weight
+        else:
             cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
             cwk = co[0].weight.detach().permute(2, 3, 4, 0, 1).reshape(27, self.hidden_channels, 2 * self.dim).contiguous()
-            w3 = co[3].weight.reshape(3, self.hidden_channels)
+            cwp = None
+        if imgs is not None:
             return ops.FusedCrossBlockFn.apply(
                 x.contiguous(), xa.contiguous(), s1, s2, self.num_heads, _current(imgs[0]), _current(imgs[1]),
                 self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight, a.proj.bias,
                 cw, cwk, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
-                self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
-        cw = co[0].weight.permute(2, 3, 4, 1, 0).reshape(27, 2 * self.dim, self.hidden_channels).contiguous()
-        cwk = None
-        if ops.N.get_gemm_mode() == 1:      # tcgen05 forward reads the weight as [tap][out][in]
-            cwk = co[0].weight.detach().permute(2, 3, 4, 0, 1).reshape(27, self.hidden_channels, 2 * self.dim).contiguous()
-        w3 = co[3].weight.reshape(3, self.hidden_channels)
+                self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, cwp)
+        if ops.N.get_gemm_mode() != 1:      # only the tcgen05 forward reads the weight as [tap][out][in]
+            cwk = None
         return ops.CrossBlockFn.apply(
             x.contiguous(), xa.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
             a.proj.bias, cw, cwk, co[0].bias, co[1].norm.weight, co[1].norm.bias, w3, self.norm2.weight, self.norm2.bias,
-            self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()))
+            self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()), cwp)
 
 
 class TransformerBlock3D(nn.Module):
@@ -573,7 +591,9 @@ class MicFormer(nn.Module):
                 if isinstance(m, (CrossTransformerBlock3D, TransformerBlock3D)) and (m.dim, m.dim // m.num_heads) in fused.FUSED_ATTN \
                         and tuple(m.window_size) == (2, 2, 2):
                     imgs.append(_attn_images(m.cross_attn if isinstance(m, CrossTransformerBlock3D) else m.self_attn))
-        fused.model_refresh([i for i in imgs if i is not None])
+        convs = [_conv_layouts(m.conv_offset[0]) for m in self.modules()
+                 if isinstance(m, CrossTransformerBlock3D) and m.conv_offset[0].weight.is_contiguous()] if (vol.is_cuda and _CONV_LAYOUTS) else []
+        fused.model_refresh([i for i in imgs if i is not None], convs)
         moving = self.patch_embed(vol, 0)
         fixed = self.patch_embed(vol, 1)
         feats_m, feats_f = [], []

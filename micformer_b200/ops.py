@@ -98,8 +98,34 @@ _AUX_ON = _os.environ.get("MICFORMER_AUX_STREAM", "1") != "0"
 _AUX = {}
 
 
+_DEFER_ON = _os.environ.get("MICFORMER_DEFER_JOIN", "0") == "1"      # measured: no gain (21.32 vs 21.24 ms/step), off by default
+_PENDING = {}          # calling stream -> (stream, event of its side branch's last kernel, tensors those kernels read)
+_FLUSH_QUEUED = [False]
+
+
+def flush_side_branches() -> None:
+    """Join every deferred side branch into the stream that forked it (end of backward; before a gradient exchange)."""
+    _FLUSH_QUEUED[0] = False
+    here = torch.cuda.current_stream() if _PENDING else None
+    for key in list(_PENDING):
+        cur, ev, keep = _PENDING.pop(key)
+        cur.wait_event(ev)
+        # the engine callback runs on the caller's stream AFTER autograd has joined its leaf streams into it: join directly too
+        if here is not None and here != cur:
+            here.wait_event(ev)
+        keep.clear()
+
+
 class side_branch:
-    """with side_branch() as sb: sb.run(fn, *args) ... ; joins on exit"""
+    """with side_branch() as sb: sb.run(fn, *args) ... ; joins on exit.
+
+    ``defer=True`` (block backward functions, whose parameters are used once per forward): the join is postponed by one
+    block -- the exit only joins the PREVIOUS deferred branch of this stream, so the weight-gradient kernels of block k
+    run under the data-gradient chain of block k-1; the last one is joined by an autograd-engine callback at the end of
+    the backward pass (``flush_side_branches``).  The tensors the side kernels read stay referenced until their join."""
+
+    def __init__(self, defer: bool = False):
+        self.defer = defer and _DEFER_ON and _AUX_ON
 
     def __enter__(self):
         self.cur = torch.cuda.current_stream()
@@ -112,6 +138,7 @@ class side_branch:
             if aux is None:
                 aux = _AUX[key] = torch.cuda.Stream(device=self.cur.device)
             self.aux = aux
+            self.key = key
         else:
             self.aux = None
         return self
@@ -129,8 +156,29 @@ class side_branch:
         self.keep.extend(t for t in tensors if t is not None)
 
     def __exit__(self, *exc):
-        if self.aux is not None and self.used:
-            self.cur.wait_stream(self.aux)
+        if self.aux is None or not self.used:
+            self.keep.clear()
+            return
+        if self.defer and exc[0] is None:
+            try:
+                if not _FLUSH_QUEUED[0]:
+                    torch.autograd.Variable._execution_engine.queue_callback(flush_side_branches)
+                    _FLUSH_QUEUED[0] = True
+            except RuntimeError:           # not inside an autograd backward pass: nothing would join the branch later
+                self.cur.wait_stream(self.aux)
+                self.keep.clear()
+                return
+            prev = _PENDING.pop(self.key, None)
+            if prev is not None:
+                self.cur.wait_event(prev[1])
+                prev[2].clear()
+            _PENDING[self.key] = (self.cur, self.aux.record_event(), self.keep)
+            self.keep = []
+            return
+        prev = _PENDING.pop(self.key, None)      # an immediate join also covers anything deferred earlier on this stream
+        if prev is not None:
+            prev[2].clear()
+        self.cur.wait_stream(self.aux)
         self.keep.clear()
 
 
@@ -290,15 +338,22 @@ def conv3_bwd_data(dy: Tensor, wt: Tensor, dx0: Tensor, acc0: bool, dx1: Optiona
 
 
 def conv3_bwd_weight(dy: Tensor, x0: Tensor, x1: Optional[Tensor], dwt: Tensor, dbias: Optional[Tensor], B, dims, Co: int,
-                     dy_ncdhw: bool) -> None:
-    """dwt[27][Cin][Co] += , dbias[Co] += : TF32 mma.sync kernel in tensor-core mode, else the fp32 CUDA-core kernel."""
+                     dy_ncdhw: bool, native: bool = False) -> None:
+    """dwt += , dbias[Co] += : TF32 mma.sync kernel in tensor-core mode, else the fp32 CUDA-core kernel.
+    ``native``: dwt is the Conv3d parameter's own (Co, Cin, 3, 3, 3) gradient; otherwise the permuted [27][Cin][Co] buffer."""
     D, H, W = dims
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     if N.get_gemm_mode() == 1:
         if N.try_call("mic_conv3_mma_bwd_weight", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(dwt), N.ptr(dbias), B, D, H, W,
-                      Co, int(dy_ncdhw)):
+                      Co, int(dy_ncdhw), int(native)):
             return
+    if native:       # the CUDA-core kernel writes [27][Cin][Co]: permute-add (exact-fp32 mode / shapes the mma kernel declines)
+        tmp = torch.zeros(27, C0 + C1, Co, device=dy.device, dtype=torch.float32)
+        N.call("mic_conv3_bwd_weight", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(tmp), N.ptr(dbias), B, D, H, W, D, H, W, Co,
+               int(dy_ncdhw))
+        dwt.view(Co, C0 + C1, 27).add_(tmp.permute(2, 1, 0))
+        return
     N.call("mic_conv3_bwd_weight", N.ptr(dy), N.ptr(x0), C0, N.ptr(x1), C1, N.ptr(dwt), N.ptr(dbias), B, D, H, W, D, H, W, Co,
            int(dy_ncdhw))
 
@@ -444,7 +499,7 @@ class SelfBlockFn(torch.autograd.Function):
         C = x.shape[-1]
         P = B * pdims[0] * pdims[1] * pdims[2]
         dy = dy.contiguous()
-        with zero_arena(12 * C * C + 128 * C + 4096, x), side_branch() as sb:
+        with zero_arena(12 * C * C + 128 * C + 4096, x), side_branch(defer=True) as sb:
             dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b,
                                                                ctx.mlp_img)
             do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
@@ -470,7 +525,7 @@ class CrossBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xa, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cwk, cb, lnw, lnb, w3, n2w,
-                n2b, f1w, f1b, f2w, f2b, mlp_img=None):
+                n2b, f1w, f1b, f2w, f2b, mlp_img=None, cwp=None):
         N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
@@ -499,6 +554,7 @@ class CrossBlockFn(torch.autograd.Function):
         ctx.meta = (dims, pdims, ws, padded, heads, s1 is not None, s2 is not None)
         ctx.biases = (n1b, qb, kvb, pb, cb, n2b, f1b, f2b)
         ctx.mlp_img = mlp_img
+        ctx.cwp = cwp       # conv_offset.0.weight itself: its gradient is written in the parameter's layout (cw, cwk: layout copies)
         return y
 
     @staticmethod
@@ -519,7 +575,7 @@ class CrossBlockFn(torch.autograd.Function):
         P = B * Dp * Hp * Wp
         HC = cw.shape[-1]
         dy = dy.contiguous()
-        with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192, x), side_branch() as sb:
+        with zero_arena(12 * C * C + 27 * 2 * C * HC + 128 * C + 8192 + P * C, x), side_branch(defer=True) as sb:
             dx1, dn2w, dn2b, df1w, df1b, df2w, df2b = _mlp_bwd(sb, dy, x1, mlp_saved, n2w, f1w, f2w, s2, dims, n2b, f1b, f2b,
                                                                ctx.mlp_img)
             do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
@@ -539,18 +595,20 @@ class CrossBlockFn(torch.autograd.Function):
             N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
                    N.ptr(dlnb), N.ptr(dw3), B, Dp, Hp, Wp, HC, LN_EPS)
             dlnw, dlnb = _gret(lnw, dlnw), _gret(lnb, dlnb)
-            dcw = _zeros(tuple(cw.shape), x)
+            cwp = ctx.cwp
+            dcw = _zeros(tuple(cw.shape), x) if cwp is None else (_acc(cwp) if _acc(cwp) is not None else _zeros(tuple(cwp.shape), x))
             dcb = _acc(cb) if _acc(cb) is not None else _zeros((HC,), x)
             sb.hold(dh16, xn_p, xa_p)
-            sb.run(conv3_bwd_weight, dh16, xn_p, xa_p, dcw, dcb, B, (Dp, Hp, Wp), HC, False)
+            sb.run(conv3_bwd_weight, dh16, xn_p, xa_p, dcw, dcb, B, (Dp, Hp, Wp), HC, False, cwp is not None)
             conv3_bwd_data(dh16, cw, dxn_p.view(B, Dp, Hp, Wp, C), True, dxa_p, True, B, (Dp, Hp, Wp), HC, False)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         if padded:
             dxa = dxa_p[:, :D, :H, :W, :].contiguous()
         else:
             dxa = dxa_p
-        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw, None, _gret(cb, dcb), dlnw, dlnb, dw3,
-                dn2w, dn2b, df1w, df1b, df2w, df2b, None)
+        dcw_old, dcw_new = (dcw, None) if cwp is None else (None, _gret(cwp, dcw))
+        return (dx, dxa, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dcw_old, None, _gret(cb, dcb), dlnw, dlnb,
+                dw3, dn2w, dn2b, df1w, df1b, df2w, df2b, None, dcw_new)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -614,8 +672,9 @@ class FusedCrossBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, xa, s1, s2, heads, aimg, mimg, n1w, n1b, qw, qb, kvw, kvb, pw, pb, cw, cwk, cb, lnw, lnb, w3, n2w,
-                n2b, f1w, f1b, f2w, f2b):
+                n2b, f1w, f1b, f2w, f2b, cwp=None):
         N.check_cuda_f32(x, xa, n1w, qw, kvw, pw, cw, w3, f1w, f2w)
+        ctx.cwp = cwp
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
         P = B * D * H * W
@@ -652,7 +711,7 @@ class FusedCrossBlockFn(torch.autograd.Function):
         P = B * D * H * W
         HC = cw.shape[-1]
         dy = dy.contiguous()
-        with zero_arena(12 * C * C + 27 * 2 * C * HC + 64 * C + 8192 + P * C, x), side_branch() as sb:
+        with zero_arena(12 * C * C + 27 * 2 * C * HC + 64 * C + 8192 + P * C, x), side_branch(defer=True) as sb:
             mg, mret = _grad_bufs((n2w, n2b, f1w, f1b, f2w, f2b), x)
             dx1 = F_.mlp_block_bwd(dy, x1, mimg, n2w, n2b, f1b, s2, D * H * W, LN_EPS, *mg)
             # attention half: dxq = dx1 + LN1'(dq Wq) (the q path of norm1), dsamp = [dk|dv] Wkv; norm1's gradients through the
@@ -668,10 +727,11 @@ class FusedCrossBlockFn(torch.autograd.Function):
             dw3 = _zeros((3, HC), x)
             N.call("mic_offset_head_bwd", N.ptr(dpos), N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(dh16), N.ptr(dlnw),
                    N.ptr(dlnb), N.ptr(dw3), B, D, H, W, HC, LN_EPS)
-            dcw = _zeros(tuple(cw.shape), x)
+            cwp = ctx.cwp
+            dcw = _zeros(tuple(cw.shape), x) if cwp is None else (_acc(cwp) if _acc(cwp) is not None else _zeros(tuple(cwp.shape), x))
             dcb = _acc(cb) if _acc(cb) is not None else _zeros((HC,), x)
             sb.hold(dh16, xn, xa)
-            sb.run(conv3_bwd_weight, dh16, xn, xa, dcw, dcb, B, (D, H, W), HC, False)
+            sb.run(conv3_bwd_weight, dh16, xn, xa, dcw, dcb, B, (D, H, W), HC, False, cwp is not None)
             dxn = _empty((B, D, H, W, C), x)
             conv3_bwd_data(dh16, cw, dxn, False, dxa, True, B, (D, H, W), HC, False)
             # second use of norm1's backward: the gradient that reached LN(x) through the offset conv
@@ -679,8 +739,9 @@ class FusedCrossBlockFn(torch.autograd.Function):
             if _acc(n1w) is None:                    # no arena: add the two contributions of norm1's parameters
                 aret[0] = aret[0] + dn1w2
                 aret[1] = aret[1] + dn1b2
-        return (dx, dxa, None, None, None, None, None, *aret, dcw, None, _gret(cb, dcb), _gret(lnw, dlnw), _gret(lnb, dlnb),
-                dw3, *mret)
+        dcw_old, dcw_new = (dcw, None) if cwp is None else (None, _gret(cwp, dcw))
+        return (dx, dxa, None, None, None, None, None, *aret, dcw_old, None, _gret(cb, dcb), _gret(lnw, dlnw), _gret(lnb, dlnb),
+                dw3, *mret, dcw_new)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -44,6 +44,8 @@ class GradSync:
     def _on_bottleneck_grad(self, grad):
         if self.world <= 1:
             return grad
+        from . import ops
+        ops.flush_side_branches()                  # deferred weight-gradient branches of the decoder blocks join their streams first
         cur = torch.cuda.current_stream()
         self._pending += 1
         if self._pending < 2:                      # first of the two modality streams: remember where its backward stands

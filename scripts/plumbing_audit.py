@@ -46,11 +46,12 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True, record_shapes=True) as prof:
         step()
         torch.cuda.synchronize()
     # cpu op events that own at least one CUDA kernel, keyed by (op name, first frame inside this repository)
     sites = collections.Counter()
+    shapes = collections.Counter()
     kern = collections.Counter()
     for ev in prof.events():
         if ev.device_type != torch.autograd.DeviceType.CPU or not ev.name.startswith("aten::"):
@@ -62,9 +63,13 @@ def main():
         frame = next((s for s in ev.stack if "micformer_b200" in s or "bench.py" in s or "scripts/" in s), "(autograd engine / no python frame)")
         sites[(ev.name, frame.strip())] += nk
         kern[ev.name] += nk
+        shapes[(ev.name, str(ev.input_shapes)[:90], (ev.stack[0].strip()[-70:] if ev.stack else ""))] += nk
     print("aten ops that launched kernels in one step:", dict(kern))
     for (name, frame), n in sites.most_common(60):
         print(f"{n:5d}  {name:28s} {frame}")
+    print("by input shapes (and innermost recorded frame):")
+    for (name, shp, fr), n in shapes.most_common(70):
+        print(f"{n:5d}  {name:14s} {shp:90s} {fr}")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity2.py tests/test_gpu_tc.py -q -x 2>&1 | tail -3 | cut -c1-250
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --no-attn-isolation --no-kernel-pass $EXTRA > gpurun_out/r2x_bench_$name.json 2> gpurun_out/r2x_bench_$name.err; python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/r2x_bench_$name.json')); print('$name', round(d['ms_per_step'],3), d['gpu_launches'])
+except Exception as e: print('$name failed', e)
+PY
+}
+run lay0 MICFORMER_CONV_LAYOUTS=0
+run lay1 MICFORMER_CONV_LAYOUTS=1
+run lay0b MICFORMER_CONV_LAYOUTS=0
+run lay1b MICFORMER_CONV_LAYOUTS=1
+python scripts/time_small.py 2>&1 | grep "offset branch"

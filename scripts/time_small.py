@@ -102,7 +102,9 @@ for (S, C, heads) in [(32, 48, 3), (16, 96, 6), (8, 192, 12), (4, 384, 24)]:
     t_ohb = timeit(f_ohb)
     dcw = torch.zeros_like(cw); dcb = torch.zeros(HC, device=dev)
     t_cw = timeit(lambda: ops.conv3_bwd_weight(dh16, xn, xa, dcw, dcb, B, (S, S, S), HC, False))
+    dcn = torch.zeros(HC, 2 * C, 3, 3, 3, device=dev)
+    t_cwn = timeit(lambda: ops.conv3_bwd_weight(dh16, xn, xa, dcn, dcb, B, (S, S, S), HC, False, True))
     dxn = torch.empty(B, S, S, S, C, device=dev)
     t_cd = timeit(lambda: ops.conv3_bwd_data(dh16, cw, dxn, False, dxa, True, B, (S, S, S), HC, False))
     print(f"                 offset branch: conv fwd {t_cf:6.1f}  head fwd {t_oh:6.1f}  sample fwd {t_ds:6.1f} | sample bwd {t_dsb:6.1f}  head bwd {t_ohb:6.1f}  "
-          f"conv dW {t_cw:6.1f}  conv bwd-data {t_cd:6.1f} us")
+          f"conv dW {t_cw:6.1f} (native layout {t_cwn:6.1f})  conv bwd-data {t_cd:6.1f} us")
