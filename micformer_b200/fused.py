@@ -147,6 +147,32 @@ def refresh_conv_layouts(convs: List["ConvLayouts"]) -> None:
 refresh_conv_layouts._cache = {}
 
 
+class QkvCat:
+    """q.weight (C, C) | kv.weight (2C, C) -> one (3C, C) weight and (3C,) bias, so that the unfused self-attention blocks
+    run ONE q|k|v GEMM forward and ONE data-gradient GEMM backward (two launches fewer on each block's dependent chain).
+    The buffers are persistent; all blocks of a model are refreshed by one multi-tensor copy per forward."""
+
+    def __init__(self, qw, qb, kvw, kvb):
+        c = qw.shape[0]
+        self.w = torch.empty(3 * c, qw.shape[1], device=qw.device)
+        self.b = torch.empty(3 * c, device=qw.device) if qb is not None else None
+        self.srcs = [qw, kvw] + ([qb, kvb] if qb is not None else [])
+        self.dsts = [self.w[:c], self.w[c:]] + ([self.b[:c], self.b[c:]] if qb is not None else [])
+        self._ptrs = [t.data_ptr() for t in self.srcs]
+        self.stamp = -1
+
+    def valid(self) -> bool:
+        return [t.data_ptr() for t in self.srcs] == self._ptrs
+
+    def refresh(self) -> None:
+        torch._foreach_copy_(self.dsts, self.srcs)
+
+
+def refresh_qkv_cats(cats: List["QkvCat"]) -> None:
+    if cats:
+        torch._foreach_copy_([d for c in cats for d in c.dsts], [s for c in cats for s in c.srcs])
+
+
 _epoch = 0        # bumped by every model-level refresh; an image set whose stamp equals it is current
 
 
@@ -154,7 +180,8 @@ def epoch() -> int:
     return _epoch
 
 
-def model_refresh(images: List[WeightImages], convs: Optional[List[ConvLayouts]] = None) -> None:
+def model_refresh(images: List[WeightImages], convs: Optional[List[ConvLayouts]] = None,
+                  cats: Optional[List[QkvCat]] = None) -> None:
     """Called once per model forward (the optimizer changed the weights): one launch converts all images, one more
     rewrites the operand layouts of all 3x3x3 conv weights."""
     global _epoch
@@ -166,6 +193,10 @@ def model_refresh(images: List[WeightImages], convs: Optional[List[ConvLayouts]]
     if convs:
         refresh_conv_layouts(convs)
         for c in convs:
+            c.stamp = _epoch
+    if cats:
+        refresh_qkv_cats(cats)
+        for c in cats:
             c.stamp = _epoch
 
 

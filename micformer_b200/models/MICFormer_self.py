@@ -106,6 +106,21 @@ def _conv_layouts(conv):
     return lay
 
 
+_QKV_CAT = _os.environ.get("MICFORMER_QKV_CAT", "1") != "0"
+
+
+def _qkv_cat(attn):
+    """persistent q|kv weight / bias concatenation of a WindowAttention3D for the unfused self blocks (cached on the module)"""
+    if not (_QKV_CAT and attn.q.weight.is_cuda):
+        return None
+    cat = attn.__dict__.get("_mic_cat")
+    if cat is None or not cat.valid():
+        with torch.no_grad():
+            cat = attn.__dict__["_mic_cat"] = fused.QkvCat(attn.q.weight.detach(), None if attn.q.bias is None else attn.q.bias.detach(),
+                                                           attn.kv.weight.detach(), None if attn.kv.bias is None else attn.kv.bias.detach())
+    return cat
+
+
 def _fused_block_images(block, attn, dims):
     """(attention images, MLP images) when BOTH halves of this block run as fused kernels for this geometry, else None"""
     C = block.dim
@@ -390,7 +405,7 @@ class TransformerBlock3D(nn.Module):
             x.contiguous(), s1, s2, self.num_heads, tuple(self.window_size),
             self.norm1.weight, self.norm1.bias, a.q.weight, a.q.bias, a.kv.weight, a.kv.bias, a.proj.weight,
             a.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
-            self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()))
+            self.mlp.fc2.weight, self.mlp.fc2.bias, _current(self.mlp.fused_images()), _current(_qkv_cat(a)))
 
 
 class PatchMerging(nn.Module):
@@ -593,7 +608,13 @@ class MicFormer(nn.Module):
                     imgs.append(_attn_images(m.cross_attn if isinstance(m, CrossTransformerBlock3D) else m.self_attn))
         convs = [_conv_layouts(m.conv_offset[0]) for m in self.modules()
                  if isinstance(m, CrossTransformerBlock3D) and m.conv_offset[0].weight.is_contiguous()] if (vol.is_cuda and _CONV_LAYOUTS) else []
-        fused.model_refresh([i for i in imgs if i is not None], convs)
+        cats = []
+        if vol.is_cuda and _QKV_CAT:
+            for m in self.modules():
+                if isinstance(m, TransformerBlock3D) and not (fused.enabled() and (m.dim, m.dim // m.num_heads) in fused.FUSED_ATTN
+                                                              and tuple(m.window_size) == (2, 2, 2) and m.mlp.fused_images() is not None):
+                    cats.append(_qkv_cat(m.self_attn))
+        fused.model_refresh([i for i in imgs if i is not None], convs, [c for c in cats if c is not None])
         moving = self.patch_embed(vol, 0)
         fixed = self.patch_embed(vol, 1)
         feats_m, feats_f = [], []

@@ -462,7 +462,8 @@ class SelfBlockFn(torch.autograd.Function):
     norm1.{w,b}, q.{w,b}, kv.{w,b}, proj.{w,b}, norm2.{w,b}, fc1.{w,b}, fc2.{w,b}."""
 
     @staticmethod
-    def forward(ctx, x, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, mlp_img=None):
+    def forward(ctx, x, s1, s2, heads, window, n1w, n1b, qw, qb, kvw, kvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b, mlp_img=None,
+                qkv_cat=None):
         N.check_cuda_f32(x, n1w, qw, kvw, pw, f1w, f2w)
         B, D, H, W, C = x.shape
         dims = (B, D, H, W)
@@ -471,8 +472,14 @@ class SelfBlockFn(torch.autograd.Function):
         P = B * pdims[0] * pdims[1] * pdims[2]
         xn_p, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims, pdims)
         qkv = _empty((P, 3 * C), x)
-        linear_fwd(xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
-        linear_fwd(xn_p, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
+        if qkv_cat is not None and (qkv_cat.b is not None) == (qb is not None):
+            # q and kv read the same LayerNorm output: one GEMM against the concatenated (3C, C) weight (fused.QkvCat)
+            linear_fwd(xn_p, C, qkv_cat.w, qkv_cat.b, P, 3 * C, C, out=qkv, out_col=0, ldy=3 * C)
+            ctx.wqkv = qkv_cat.w
+        else:
+            linear_fwd(xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
+            linear_fwd(xn_p, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
+            ctx.wqkv = None
         o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
         x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
         y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims, mlp_img)
@@ -506,11 +513,14 @@ class SelfBlockFn(torch.autograd.Function):
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
             dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
             dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, 2 * C, C, wp=kvw, bp=kvb, dy_col=C)
-            dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
-            linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
+            if ctx.wqkv is not None:
+                dxn_p = linear_bwd_data(dqkv, 3 * C, ctx.wqkv, P, 3 * C, C)       # reduction over q | k | v at once
+            else:
+                dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
+                linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C, out=dxn_p, lddx=C, accumulate=True)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         return (dx, None, None, None, None, dn1w, dn1b, dqw, dqb, dkvw, dkvb, dpw, dpb, dn2w, dn2b, df1w, df1b, df2w,
-                df2b, None)
+                df2b, None, None)
 
 
 class CrossBlockFn(torch.autograd.Function):
