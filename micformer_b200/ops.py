@@ -95,6 +95,7 @@ def _gret(p, t):
 import os as _os
 
 _AUX_ON = _os.environ.get("MICFORMER_AUX_STREAM", "1") != "0"
+_Q_SIDE = _os.environ.get("MICFORMER_Q_SIDE", "1") != "0"      # unfused cross blocks: q GEMM / q data gradient beside the offset branch
 _AUX = {}
 
 
@@ -114,6 +115,10 @@ def flush_side_branches() -> None:
         if here is not None and here != cur:
             here.wait_event(ev)
         keep.clear()
+
+
+def _inline(fn, *args, **kw):
+    return fn(*args, **kw)
 
 
 class side_branch:
@@ -154,6 +159,14 @@ class side_branch:
 
     def hold(self, *tensors):
         self.keep.extend(t for t in tensors if t is not None)
+
+    def mark(self):
+        """event after the side kernels launched so far (None without an auxiliary stream): ``wait(mark)`` joins just those"""
+        return self.aux.record_event() if (self.aux is not None and self.used) else None
+
+    def wait(self, ev) -> None:
+        if ev is not None:
+            self.cur.wait_event(ev)
 
     def __exit__(self, *exc):
         if self.aux is None or not self.used:
@@ -547,14 +560,17 @@ class CrossBlockFn(torch.autograd.Function):
         xn_p, mean1, rstd1 = ln_fwd(x, None, n1w, n1b, dims, pdims)
         xa_p = pad_grid(xa, dims, pdims) if padded else xa
         h16 = _empty((P, HC), x)
-        conv3_fwd(xn_p, xa_p, cw, cwk, cb, h16, B, (Dp, Hp, Wp), HC, False)
-        pos = _empty((P, 3), x)
-        N.call("mic_offset_head_fwd", N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(pos), B, Dp, Hp, Wp, HC, LN_EPS)
-        samp = _empty((P, C), x)
-        N.call("mic_deform_sample_fwd", N.ptr(xa_p), N.ptr(pos), N.ptr(samp), B, Dp, Hp, Wp, Dp, Hp, Wp, C)
         qkv = _empty((P, 3 * C), x)
-        linear_fwd(xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
-        linear_fwd(samp, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
+        with side_branch() as sb:
+            # q depends only on LN(x): its GEMM runs beside the offset branch (conv -> head -> resampling) instead of after it
+            sb.hold(xn_p, qkv)
+            (sb.run if _Q_SIDE else _inline)(linear_fwd, xn_p, C, qw, qb, P, C, C, out=qkv, out_col=0, ldy=3 * C)
+            conv3_fwd(xn_p, xa_p, cw, cwk, cb, h16, B, (Dp, Hp, Wp), HC, False)
+            pos = _empty((P, 3), x)
+            N.call("mic_offset_head_fwd", N.ptr(h16), N.ptr(lnw), N.ptr(lnb), N.ptr(w3), N.ptr(pos), B, Dp, Hp, Wp, HC, LN_EPS)
+            samp = _empty((P, C), x)
+            N.call("mic_deform_sample_fwd", N.ptr(xa_p), N.ptr(pos), N.ptr(samp), B, Dp, Hp, Wp, Dp, Hp, Wp, C)
+            linear_fwd(samp, C, kvw, kvb, P, 2 * C, C, out=qkv, out_col=C, ldy=3 * C)
         o_p, lse = window_attn_fwd(qkv, C, heads, B, pdims, ws)
         x1 = _proj_residual_fwd(x, o_p, pw, pb, s1, dims, pdims, padded)
         y, mlp_saved = _mlp_fwd(x1, n2w, n2b, f1w, f1b, f2w, f2b, s2, dims, mlp_img)
@@ -590,9 +606,14 @@ class CrossBlockFn(torch.autograd.Function):
                                                                ctx.mlp_img)
             do_p, dpw, dpb = _proj_residual_bwd(sb, dx1, o_p, pw, s1, dims, pdims, padded, pb)
             dqkv = window_attn_bwd(qkv, o_p, do_p, lse, C, heads, B, pdims, ws)
+            # the q path's data gradient only meets the offset branch again at the conv's backward-data (which accumulates
+            # into dxn_p): it runs on the side branch, ahead of the q / kv weight gradients
+            dxn_p = _empty((P, C), x)
+            sb.hold(dqkv, dxn_p)
+            (sb.run if _Q_SIDE else _inline)(linear_bwd_data, dqkv, 3 * C, qw, P, C, C, out=dxn_p, lddx=C)
+            dxn_ready = sb.mark() if _Q_SIDE else None
             dqw, dqb = linear_bwd_weight_side(sb, dqkv, 3 * C, xn_p, C, P, C, C, wp=qw, bp=qb)
             dkvw, dkvb = linear_bwd_weight_side(sb, dqkv, 3 * C, samp, C, P, 2 * C, C, wp=kvw, bp=kvb, dy_col=C)
-            dxn_p = linear_bwd_data(dqkv, 3 * C, qw, P, C, C)
             dsamp = linear_bwd_data(dqkv, 3 * C, kvw, P, 2 * C, C, dy_col=C)
             dxa_p = _zeros((B, Dp, Hp, Wp, C), x)
             dpos = _empty((P, 3), x)
@@ -610,6 +631,7 @@ class CrossBlockFn(torch.autograd.Function):
             dcb = _acc(cb) if _acc(cb) is not None else _zeros((HC,), x)
             sb.hold(dh16, xn_p, xa_p)
             sb.run(conv3_bwd_weight, dh16, xn_p, xa_p, dcw, dcb, B, (Dp, Hp, Wp), HC, False, cwp is not None)
+            sb.wait(dxn_ready)                 # dq Wq is in dxn_p
             conv3_bwd_data(dh16, cw, dxn_p.view(B, Dp, Hp, Wp, C), True, dxa_p, True, B, (Dp, Hp, Wp), HC, False)
             dx, _, dn1w, dn1b = ln_bwd(dxn_p, x, None, n1w, mean1, rstd1, dx1, None, dims, pdims, beta=n1b)
         if padded:
