@@ -57,8 +57,9 @@ def cfg_of(name):
 
 WORKLOADS = {"train": "MicFormer train config Head(embed_dim=48,num_classes=8,window=2^3,depths 2-2-6-2)",
              "w7": "MicFormer Head(embed_dim=96,num_classes=8,window=7^3,depths 2-2-6-2)"}
-DTYPE = ("f32 storage; tensor-core products: split-bf16 (hi+lo, 3 MMAs, ~2^-17) in the fused stage-0 blocks, 3xTF32 forward / "
-         "TF32 backward GEMMs and convs elsewhere; fp32 accumulate, fp32 LayerNorm / softmax / GELU / loss / Adam")
+DTYPE = ("f32 storage; tensor-core products: split-bf16 (hi+lo, 3 MMAs, ~2^-17) in the fused stage-0 blocks and the forward GEMMs "
+         "(3xTF32 where a weight is read transposed), single-pass TF32 in the backward GEMMs and the 3x3x3 convs; fp32 accumulate, "
+         "fp32 LayerNorm / softmax / GELU / loss / Adam")
 
 
 def config_of(args):
