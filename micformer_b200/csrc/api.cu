@@ -36,6 +36,9 @@ int tc_linear_bwd_weight(const float*, int, const float*, int, float*, int, int,
 // window_attn_tc.cu (tcgen05; large windows, head_dim 32)
 int tc_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int, int,
                        int, int, int, float, cudaStream_t);
+// window_attn_tc_bwd.cu (tcgen05; large windows, head_dim 32)
+int tc_window_attn_bwd(const float*, int, const float*, const float*, int, const float*, const float*, int, const float*,
+                       float*, int, float*, float*, int, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 // window_attn.cu
 int simt_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int,
                          int, int, int, int, float, cudaStream_t);
@@ -142,6 +145,13 @@ extern "C" int mic_window_attn_bwd(const float* q, int ldq, const float* k, cons
                                    float* dv, int lddkv, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh,
                                    int ww, float scale, void* stream) {
     MIC_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv, "window_attn_bwd: null pointer");
+    // MICFORMER_ATTN_BWD_SIMT=1 keeps the exact CUDA-core backward for large windows too
+    static const bool force_simt = []() { const char* e = getenv("MICFORMER_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();
+    if (g_gemm_mode.load() == 1 && !force_simt) {
+        int rc = tc_window_attn_bwd(q, ldq, k, v, ldkv, out, dout, ldo, lse, dq, lddq, dk, dv, lddkv, B, Dp, Hp, Wp, heads, hd,
+                                    wd, wh, ww, scale, (cudaStream_t)stream);
+        if (rc != MIC_ERR_UNSUPPORTED) return rc;
+    }
     return simt_window_attn_bwd(q, ldq, k, v, ldkv, out, dout, ldo, lse, dq, lddq, dk, dv, lddkv, B, Dp, Hp, Wp, heads, hd,
                                 wd, wh, ww, scale, (cudaStream_t)stream);
 }
