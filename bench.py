@@ -209,15 +209,39 @@ def secondary_w7(dev, args, steps=10):
     for _ in range(3):
         one()
     torch.cuda.synchronize()
+    # the same treatment as the headline step: the whole step in ONE CUDA graph (eager, this model's ~3400 launches cost
+    # ~30 ms of host time per step: 99 ms eager vs 68 ms replayed, gpurun_out r2bd / r2bf)
+    graph, loss = None, None
+    if args.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = crit(model(x), lab)
+            loss.backward()
+            opt.step()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = one()
+        if graph is not None:
+            graph.replay()
+        else:
+            loss = one()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"workload": WORKLOADS["w7"], "volumes_per_step": args.batch, "steps": steps, "warmup": 3, "ms_per_step": round(ms, 3),
-            "volumes_per_s": round(args.batch / ms * 1e3, 2), "loss": round(float(loss.detach()), 6),
-            "note": "eager launches (no CUDA graph); attention forward on tcgen05, backward on CUDA cores"}
+    out = {"workload": WORKLOADS["w7"], "volumes_per_step": args.batch, "steps": steps, "warmup": 3, "ms_per_step": round(ms, 3),
+           "volumes_per_s": round(args.batch / ms * 1e3, 2), "loss": round(float(loss.detach()), 6), "cuda_graph": graph is not None,
+           "note": "window attention forward and backward on tcgen05 (343-token windows)"}
+    del graph
+    return out
 
 
 def eager_cuda(dev, cfg, B, S, train_mode, steps=3):
@@ -351,7 +375,8 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         _native.reset_launch_count()
-        with torch.cuda.graph(graph):
+        cap_stream = torch.cuda.Stream(priority=-1) if os.environ.get("MICFORMER_STREAM_PRIO", "0") == "1" else None
+        with torch.cuda.graph(graph, stream=cap_stream):
             if arena is not None:
                 arena.zero()                       # one memset node; without the arena the grads are re-created per replay
             loss_static = crit(model(x_d), lab_d)
@@ -512,7 +537,26 @@ def run_ours(args):
                 "algorithmic_gbs": round(abytes / ams / 1e6, 1),
                 "frac_of_hbm_peak": round(abytes / ams / 1e6 / pk["hbm_gbs"], 4),
                 "note": "fp32 Q/K/V/O make this shape HBM-bound below the tensor ridge: 2.16 GB / measured copy bandwidth = 0.33 ms floor"}
-        del qkv
+        # the same shape's backward (tcgen05: csrc/window_attn_tc_bwd.cu): dQ, dK, dV from Q, K, V, O, dO, lse
+        o_a, lse_a = _ops.window_attn_fwd(qkv, Ca, Ha, Bw, (7, 7, 7), (7, 7, 7))
+        do_a = torch.randn_like(o_a)
+        for _ in range(3):
+            _ops.window_attn_bwd(qkv, o_a, do_a, lse_a, Ca, Ha, Bw, (7, 7, 7), (7, 7, 7))
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(5):
+            _ops.window_attn_bwd(qkv, o_a, do_a, lse_a, Ca, Ha, Bw, (7, 7, 7), (7, 7, 7))
+        a1.record(); torch.cuda.synchronize()
+        bms = a0.elapsed_time(a1) / 5
+        bflops = 2.5 * aflops                                     # five 343 x 343 x 32 products per (window, head)
+        bbytes = 4.0 * (8 * Bw * 343 * Ca + Bw * 343 * Ha)       # q, k, v, o, do in; dq, dk, dv out; lse
+        attn["backward"] = {"ms": round(bms, 4), "tflops": round(bflops / bms / 1e9, 1),
+                            "frac_of_tf32_peak": round(bflops / bms / 1e9 / tf32_peak, 4),
+                            "algorithmic_gbs": round(bbytes / bms / 1e6, 1),
+                            "frac_of_hbm_peak": round(bbytes / bms / 1e6 / pk["hbm_gbs"], 4),
+                            "note": "algorithmic flops (5 products); the kernel runs 8 (scores in both orientations) -- "
+                                    "A operands of the accumulating products come from TMEM"}
+        del qkv, o_a, lse_a, do_a
     if world > 1:
         dist.barrier()
 

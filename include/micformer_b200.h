@@ -79,9 +79,11 @@ int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, fl
  *      (:37-50,:117-132,:193-200,:251-258) without materialising windows or scores.  q/k/v/out are token-grid
  *      tensors (B,Dp,Hp,Wp,heads*hd) with row strides ldq/ldkv/ldo (k and v usually point into one kv buffer);
  *      lse (rows, heads) is saved for the backward.  No mask, no relative-position bias.
- *      Dispatch (forward): tensor-core mode + head_dim 32 + 128..352 tokens per window + q/k/v adjacent in one (P,3C)
- *      buffer -> the tcgen05/TMA FlashAttention-style kernels (S/P in TMEM; two softmax pipelines above 192 tokens);
- *      otherwise the exact-fp32 CUDA-core kernel (8-token windows of the train config, every backward). */
+ *      Dispatch: tensor-core mode + head_dim 32 + 128..352 tokens per window + q/k/v adjacent in one (P,3C)
+ *      buffer -> the tcgen05/TMA FlashAttention-style kernels (forward: S/P in TMEM, two softmax pipelines above 192
+ *      tokens; backward: scores recomputed in both orientations, P / dS fed to the dQ / dK / dV products as TMEM A
+ *      operands, csrc/window_attn_tc_bwd.cu); otherwise the exact-fp32 CUDA-core kernels (8-token windows of the
+ *      train config).  MICFORMER_ATTN_BWD_SIMT=1 keeps the CUDA-core backward for large windows too. */
 int mic_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo,
                         float* lse, int B, int Dp, int Hp, int Wp, int heads, int hd, int wd, int wh, int ww,
                         float scale, void* stream);

@@ -464,7 +464,10 @@ window_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapQK,    // qkv r
             const int egrp = (pass - 1) & 1;
             if (tr) btrace(g * 8 + 4);
             if (epi && x == egrp) {
-                bbar_arrive(&p_ready[b]);                        // nothing of this chunk is mine
+                // nothing of this chunk is mine -- but its s_full phase is still observed: a waiter that skips a phase
+                // would take the NEXT use of this parity for complete the moment it looks
+                bbar_wait(&s_full[b], (uint32_t)((g >> 1) & 1));
+                bbar_arrive(&p_ready[b]);
                 epilogue(pass - 1, 0, 2, true);
                 if (tr) btrace(g * 8 + 7);
             } else {

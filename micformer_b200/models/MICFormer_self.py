@@ -14,6 +14,7 @@ from __future__ import annotations
 from functools import reduce
 from operator import mul
 
+import os
 import torch
 import torch.nn as nn
 
@@ -59,7 +60,9 @@ _SIDE = {}
 def _side_stream(device):
     st = _SIDE.get(device)
     if st is None:
-        st = _SIDE[device] = torch.cuda.Stream(device=device)
+        # MICFORMER_STREAM_PRIO=1: the modality stream (like the caller's stream, see bench.py) outranks the auxiliary
+        # weight-gradient streams of ops.side_branch, so pending CTAs of the dependent chain are placed first
+        st = _SIDE[device] = torch.cuda.Stream(device=device, priority=-1 if os.environ.get("MICFORMER_STREAM_PRIO", "0") == "1" else 0)
     return st
 
 

@@ -15,3 +15,11 @@ for _ in range(5): ops.window_attn_fwd(qkv, C, heads, Bw, (7, 7, 7), (7, 7, 7))
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print(f"config4 x{Bw}: {ms:.3f} ms  {4.0 * Bw * heads * 343 * 343 * 32 / ms / 1e9:.1f} TFLOP/s")
+if len(sys.argv) > 2 and sys.argv[2] == "bwd":          # the same shape's tcgen05 backward
+    do = torch.randn(Bw * 343, C, device="cuda")
+    for _ in range(2): ops.window_attn_bwd(qkv, o, do, lse, C, heads, Bw, (7, 7, 7), (7, 7, 7))
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5): ops.window_attn_bwd(qkv, o, do, lse, C, heads, Bw, (7, 7, 7), (7, 7, 7))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"config4 backward x{Bw}: {ms:.3f} ms  {10.0 * Bw * heads * 343 * 343 * 32 / ms / 1e9:.1f} TFLOP/s (algorithmic, 5 products)")
