@@ -12,6 +12,11 @@
 // (128 x Co) are staged once in shared memory, rounded to nearest TF32; each warp then runs 16 k-steps (one 8-wide
 // x row of the brick each) of 3 taps x 2 channel tiles x (Co/8) MMAs on register accumulators that live across all
 // bricks and are flushed once with atomics.  Row strides (40 / 24 floats) make all fragment loads conflict-free.
+//
+// Measured bound (round 2, gpurun r2bj): the kernel sits on the legacy mma.sync TF32 issue rate of this chip (~1
+// m16n8k8 per 9-11 SM clocks: 864 MMAs per brick in ~9.4k clocks), NOT on its shared-memory fragment loads -- a variant
+// that applied every x row to all nine (tz, ty) taps (2 LDS per MMA instead of 4.3, cp.async double-buffered bricks, one
+// CTA per SM) ran out_conv's gradient in 1.34 ms against 1.06 ms here and was dropped.
 #include "common.cuh"
 
 namespace mic {

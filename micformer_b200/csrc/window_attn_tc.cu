@@ -499,7 +499,9 @@ __device__ __forceinline__ void softmax_block(uint32_t taddr, int nch, int valid
 // Single-pass variant for a row whose shift mb is known up front (see the Cauchy-Schwarz bound in the kernel): every chunk
 // is read from TMEM exactly once.  Chunk 0 may already sit in va.
 __device__ __forceinline__ float exp_block(uint32_t taddr, int nch, int valid, float sc, float mb, uint32_t (&va)[32],
-                                           uint32_t (&vb)[32], bool va_loaded) {
+                                           uint32_t (&vb)[32], bool va_loaded, uint64_t* pub = nullptr) {
+    // pub (two-issuer kernel): arrive there once the first three chunks (96 columns of P) are in TMEM, so that their
+    // P V products are issued while the rest of the block is still being exponentiated
     float l = 0.f;
     if (!va_loaded) {
         tld32_nowait(taddr, va);
@@ -511,6 +513,10 @@ __device__ __forceinline__ float exp_block(uint32_t taddr, int nch, int valid, f
         tst32(taddr + (uint32_t)(c * 32), va);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (pub != nullptr && c == 2 && nch > 3) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            abar_arrive(pub);
+        }
         if (c + 1 < nch) {
             if (c + 2 < nch) tld32_nowait(taddr + (uint32_t)((c + 2) * 32), va);
             l += chunk_exp(vb, sc, mb, valid - (c + 1) * 32);
@@ -541,7 +547,8 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     uint64_t* s_full = rdy + AT_SLOTS;         // [2]
     uint64_t* p_full = s_full + 2;             // [2] 128 arrivals
     uint64_t* o_full = p_full + 2;             // [2]
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* pc_full = o_full + 2;            // [2][4] two-issuer kernel: P published in 96-column chunks (block 0: 2, block 1: 1-2)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(pc_full + 8);
     float* kmax2 = reinterpret_cast<float*>(tslot + 2);   // [AT_SLOTS][2]: max_j |k_j|^2 of the K tile in a slot (per conditioning warp)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -558,6 +565,7 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     if (threadIdx.x == 0) {
         for (int s = 0; s < AT_SLOTS; ++s) { abar_init(&full[s], 1); abar_init(&empty[s], ISSUERS == 1 ? 1 : nmt); abar_init(&rdy[s], 64); }
         for (int x = 0; x < 2; ++x) { abar_init(&s_full[x], 1); abar_init(&p_full[x], 128); abar_init(&o_full[x], 1); }
+        for (int i = 0; i < 8; ++i) abar_init(&pc_full[i], 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -569,6 +577,11 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
     pdl_sync();            // prologue above (ring clear, barriers, TMEM) overlaps the previous kernel
+    const int nchunk1 = w1 > 96 ? 2 : 1;       // 96-column chunks of key block 1
+    // phase trace of CTA 0 (scripts/trace_attn2.py): SM clock stamps, pointer read once (not on the issue path)
+    unsigned long long* const trp = blockIdx.x == 0 ? g_at_trace : nullptr;
+#define ATR2(slot) do { if (trp != nullptr && (slot) < 512) trp[(slot)] = (unsigned long long)clock64(); } while (0)
+#define ATR2I(n, k) do { if ((n) < 16) ATR2((n) * 16 + (k)); } while (0)      /* issuer stamps: first 16 tiles only */
 
     if (ISSUERS == 2 && warp <= 1) {
         if (lane == 0) {
@@ -592,13 +605,14 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
                 }
                 acommit(&s_full[x]);
             };
-            auto issue_pv = [&](int j, int h) {
+            // k-steps [k0, k1) of P V for key block h (8 keys per step)
+            auto issue_pv = [&](int j, int h, int k0, int k1) {
                 const uint32_t ocol = tcol + (uint32_t)(A2_B0 + 32 * h);
-                const int n = h ? ks_pv1 : A2_B0 / 8;
-                uint64_t bd = adesc(slot_addr(3 * j + 2) + (uint32_t)(h * (A2_B0 / 8) * 1024), 4096, 512, 1);
-                for (int kk = 0; kk < n; ++kk, bd += 1024 >> 4)
+                uint64_t bd = adesc(slot_addr(3 * j + 2) + (uint32_t)((h * (A2_B0 / 8) + k0) * 1024), 4096, 512, 1);
+                for (int kk = k0; kk < k1; ++kk, bd += 1024 >> 4)
                     amma_ts(ocol, tcol + (uint32_t)(kk * 8), bd, idesc_o, kk ? 1u : 0u);
             };
+            uint64_t* pc = pc_full + 4 * x;
             if (x == 0) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQK) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
@@ -632,32 +646,53 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
                     if (abar_test(&rdy[u0 % AT_SLOTS], (uint32_t)((u0 / AT_SLOTS) & 1)) &&
                         abar_test(&rdy[(u0 + 1) % AT_SLOTS], (uint32_t)(((u0 + 1) / AT_SLOTS) & 1))) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        ATR2I((int)pw, x * 8 + 0);
                         issue_s(j, mt, 0);
                         st = 1;
                     }
                 } else if (st == 1) {
-                    if (abar_test(&p_full[x], pw & 1u) &&
+                    // (each chunk barrier completes once per tile of this pipeline: parity = tiles done & 1)
+                    if (abar_test(&pc[0], pw & 1u) &&
                         abar_test(&rdy[(u0 + 2) % AT_SLOTS], (uint32_t)(((u0 + 2) / AT_SLOTS) & 1))) {
-                        ++pw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        issue_pv(j, 0);
+                        ATR2I((int)pw, x * 8 + 1);
+                        issue_pv(j, 0, 0, 12);
+                        st = 4;
+                    }
+                } else if (st == 4) {
+                    if (abar_test(&pc[1], pw & 1u)) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        ATR2I((int)pw, x * 8 + 2);
+                        issue_pv(j, 0, 12, A2_B0 / 8);
                         issue_s(j, mt, 1);
                         acommit(&empty[u0 % AT_SLOTS]);               // one of the nmt releases of Q and K
                         acommit(&empty[(u0 + 1) % AT_SLOTS]);
                         st = 2;
                     }
-                } else {
-                    if (abar_test(&p_full[x], pw & 1u)) {
-                        ++pw;
+                } else if (st == 2) {
+                    if (abar_test(&pc[2], pw & 1u)) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        issue_pv(j, 1);
-                        acommit(&o_full[x]);
-                        acommit(&empty[(u0 + 2) % AT_SLOTS]);         // one of the nmt releases of V
-                        g += 2;
-                        mt += 2;
-                        if (mt >= nmt) { mt -= nmt; ++j; }
-                        st = g < G ? 0 : 3;
+                        ATR2I((int)pw, x * 8 + 3);
+                        issue_pv(j, 1, 0, nchunk1 == 2 ? 12 : ks_pv1);
+                        st = nchunk1 == 2 ? 5 : 6;
                     }
+                } else if (st == 5) {
+                    if (abar_test(&pc[3], pw & 1u)) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        ATR2I((int)pw, x * 8 + 4);
+                        issue_pv(j, 1, 12, ks_pv1);
+                        st = 6;
+                    }
+                }
+                if (st == 6) {
+                    ATR2I((int)pw, x * 8 + 5);
+                    ++pw;
+                    acommit(&o_full[x]);
+                    acommit(&empty[(u0 + 2) % AT_SLOTS]);             // one of the nmt releases of V
+                    g += 2;
+                    mt += 2;
+                    if (mt >= nmt) { mt -= nmt; ++j; }
+                    st = g < G ? 0 : 3;
                 }
             }
         }
@@ -793,8 +828,11 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         for (int64_t g = x; g < G; g += 2, ++un) {
             const uint32_t it = blockIdx.x + (uint32_t)j * gridDim.x;
             // ---- block 0: keys [0, 192), all valid
+            const bool trs = lane == 0 && (warp == 2 || warp == 6);
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 0);
             abar_wait(&s_full[x], 0u);                // two s_full phases per tile: parities 0, 1
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 1);
             // Softmax is invariant to the shift m; it only has to keep exp2 in range.  s_ij <= |q_i| max_j |k_j|
             // (Cauchy-Schwarz) is known without reading S, so when that bound is within 2^64 of an actual score of the
             // row (taken from the first chunk), the max pass is skipped and S is read from TMEM ONCE.  Otherwise (norms
@@ -819,31 +857,50 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
             const bool row_live = mt * 128 + r < a.N;
             const bool fast = __all_sync(0xffffffffu, !row_live || (mbB - mest * a.scale_log2 <= 64.f));
             float m0, l0, m1, l1;
+            uint64_t* pc = pc_full + 4 * x;
             if (fast) {
-                l0 = exp_block(sbase, A2_B0 / 32, A2_B0, a.scale_log2, mbB, va, vb, true);
+                l0 = exp_block(sbase, A2_B0 / 32, A2_B0, a.scale_log2, mbB, va, vb, true, ISSUERS == 2 ? &pc[0] : nullptr);
                 m0 = bound;
             } else {
                 softmax_block(sbase, A2_B0 / 32, A2_B0, -INFINITY, a.scale_log2, m0, l0, va, vb);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            abar_arrive(&p_full[x]);
+            if (ISSUERS == 2) {
+                if (!fast) abar_arrive(&pc[0]);       // two-pass rows publish the whole block at once
+                abar_arrive(&pc[1]);
+            } else {
+                abar_arrive(&p_full[x]);
+            }
             // ---- block 1: keys [192, N)
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 2);
             abar_wait(&s_full[x], 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 3);
             if (fast) {
-                l1 = exp_block(sbase, nch1, v1, a.scale_log2, mbB, va, vb, false);
+                l1 = exp_block(sbase, nch1, v1, a.scale_log2, mbB, va, vb, false, ISSUERS == 2 ? &pc[2] : nullptr);
                 m1 = bound;
             } else {
                 softmax_block(sbase, nch1, v1, m0, a.scale_log2, m1, l1, va, vb);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            abar_arrive(&p_full[x]);
+            if (ISSUERS == 2) {
+                if (nchunk1 == 2) {
+                    if (!fast) abar_arrive(&pc[2]);
+                    abar_arrive(&pc[3]);
+                } else {
+                    abar_arrive(&pc[2]);
+                }
+            } else {
+                abar_arrive(&p_full[x]);
+            }
             const float mb0 = m0 * a.scale_log2, mb1 = m1 * a.scale_log2;
             // ---- epilogue: out = (O0 * alpha + O1) / (l0 * alpha + l1), alpha = 2^((m0 - m1) * scale * log2 e)
             float alpha;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(mb0 - mb1));
             const float l = fmaf(l0, alpha, l1);
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 4);
             abar_wait(&o_full[x], (uint32_t)(un & 1));
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 5);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tld32_nowait(sbase + A2_B0, va);
             tld32_nowait(sbase + A2_B0 + 32, vb);
@@ -868,6 +925,7 @@ window_attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
                                     fmaf(__uint_as_float(va[4 * t + 3]), ai, __uint_as_float(vb[4 * t + 3]) * inv));
                 a.lse[row * a.heads + head] = fmaf(__log2f(l), 0.6931471805599453f, m1 * a.scale);
             }
+            if (trs) ATR2(256 + (int)un * 16 + x * 8 + 6);
             mt += 2;
             if (mt >= nmt) { mt -= nmt; ++j; }
         }
@@ -959,7 +1017,7 @@ int tc_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, 
     a.items = (int64_t)B * a.nwd * a.nwh * a.nww * heads;
     a.scale = scale;
     a.scale_log2 = scale * 1.4426950408889634f;
-    const size_t smem = 1024 + (size_t)AT_SLOTS * AT_SLOT_BYTES + 4096 + 256;
+    const size_t smem = 1024 + (size_t)AT_SLOTS * AT_SLOT_BYTES + 4096 + 512;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(window_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -164,7 +164,9 @@ def test_tc_w7_model_logits(tc_mode):
                                                  (192, 192, 16, (8, 8, 8), False),      # stage 2: half-empty footprint, K split
                                                  (384, 384, 16, (4, 4, 4), False),      # stage 3
                                                  (24, 24, 16, (7, 7, 7), False),        # odd sizes (window-7 padded grids)
-                                                 (16, 0, 8, (3, 20, 9), True)])
+                                                 (16, 0, 8, (3, 20, 9), True),
+                                                 (24, 0, 8, (9, 10, 16), False),        # Co = 8 channels-last
+                                                 (40, 24, 8, (6, 7, 12), True)])        # two sources, two 32-channel chunks, ragged bricks
 def test_tc_conv3_fwd_bwd(tc_mode, C0, C1, Co, dims, ncdhw):
     """tcgen05 implicit-GEMM 3x3x3 conv: forward, backward-data (mirrored taps through the same kernel, accumulate
     epilogue) and backward-weight against F.conv3d autograd in fp64."""
