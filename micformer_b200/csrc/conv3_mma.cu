@@ -12,11 +12,7 @@
 // (128 x Co) are staged once in shared memory, rounded to nearest TF32; each warp then runs 16 k-steps (one 8-wide
 // x row of the brick each) of 3 taps x 2 channel tiles x (Co/8) MMAs on register accumulators that live across all
 // bricks and are flushed once with atomics.  Row strides (40 / 24 floats) make all fragment loads conflict-free.
-//
-// Measured bound (round 2, gpurun r2bj): the kernel sits on the legacy mma.sync TF32 issue rate of this chip (~1
-// m16n8k8 per 9-11 SM clocks: 864 MMAs per brick in ~9.4k clocks), NOT on its shared-memory fragment loads -- a variant
-// that applied every x row to all nine (tz, ty) taps (2 LDS per MMA instead of 4.3, cp.async double-buffered bricks, one
-// CTA per SM) ran out_conv's gradient in 1.34 ms against 1.06 ms here and was dropped.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mic {
@@ -245,6 +241,212 @@ conv3_mma_bwd_weight_kernel(const float* __restrict__ dy, const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Co = 8 variant (out_conv: 24 -> 8 classes on the 128^3 grid, the single largest weight-gradient launch of the step).
+// Legacy mma.sync issues one m16n8k8 TF32 per 2.2 clocks per SM here (scripts/ubench/mma_sync_rate.cu: 272 TFLOP/s), so
+// the 864 MMAs of a brick are ~1.9k clocks -- the kernel above spends ~9.4k per brick on dependent shared-memory loads
+// (one warp per (tz, ty) re-reads every x row for each of its k-steps, 4.3 LDS per MMA, nothing in flight across the two
+// barriers).  Here a warp owns ONE tx shift and a quarter of the 36 halo x-rows and applies each row's A fragments (8 LDS,
+// rounded once) to ALL (tz, ty) taps whose output row (hz - tz, hy - ty) lies inside the brick; all fragment loads of a
+// row are issued before its first MMA.  Bricks are double-buffered in shared memory with cp.async (zero-fill outside the
+// volume), so staging overlaps the MMAs of the previous brick in a single CTA per SM.
+constexpr int M8_THREADS = 384;                  // 12 warps: tx = warp % 3, row group = warp / 3 (rows rg, rg + 4, ..)
+constexpr int PS8 = 132;                         // NCDHW dy tile: [o][pos] row stride; bank = 4 gq + tq -> conflict-free
+constexpr int M8_DY = 128 * DS;                  // floats reserved for the dy tile (>= 8 * PS8)
+constexpr int M8_STAGE = M_NH * XS + M8_DY;      // floats per stage
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;               // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ uint32_t rn_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+// The nine halo rows RG, RG + 4, .. of one warp, fully unrolled: (hz, hy), the valid (tz, ty) taps of each row and every
+// shared-memory offset are compile-time constants (the first version of this kernel computed them at run time and was
+// instruction-issue bound: ~350 instructions per row for 18 MMAs).  xt / dt already carry the thread's fragment offsets.
+template <int RG, bool NCDHW>
+__device__ __forceinline__ void bw8_rows(const float* __restrict__ xt, const float* __restrict__ dt, float (&acc)[3][3][2][4]) {
+    constexpr int sp = NCDHW ? 1 : DS;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int ir = RG + 4 * i;
+        const int hz = ir / MH_Y, hy = ir % MH_Y;
+        const float* xr = xt + (hz * MH_Y + hy) * MH_X * XS;
+        uint32_t xa[2][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                xa[mt][hh][0] = rn_tf32_bits(xr[mt * 16 + hh * 8]);
+                xa[mt][hh][1] = rn_tf32_bits(xr[4 * XS + mt * 16 + hh * 8]);
+            }
+#pragma unroll
+        for (int tz = 0; tz < 3; ++tz)
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty) {
+                const int lz = hz - tz, ly = hy - ty;
+                if (lz >= 0 && lz < MB_Z && ly >= 0 && ly < MB_Y) {
+                    const float* db = dt + (lz * MB_Y + ly) * 8 * sp;
+                    const uint32_t b0 = rn_tf32_bits(db[0]), b1 = rn_tf32_bits(db[4 * sp]);
+                    mma_tf32(acc[tz][ty][0], xa[0][0][0], xa[0][1][0], xa[0][0][1], xa[0][1][1], b0, b1);
+                    mma_tf32(acc[tz][ty][1], xa[1][0][0], xa[1][1][0], xa[1][0][1], xa[1][1][1], b0, b1);
+                }
+            }
+    }
+}
+
+template <bool NCDHW>
+__global__ void __launch_bounds__(M8_THREADS, 1)
+conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restrict__ x0, const float* __restrict__ x1,
+                             float* __restrict__ dWt, float* __restrict__ dbias, MGeom g, int nbz, int nby, int nbx,
+                             int native) {
+    pdl_sync();
+    extern __shared__ __align__(16) float msm[];
+    float* bsum = msm + 2 * M8_STAGE;            // [8]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int c0 = blockIdx.y * 32;
+    const int Cin = g.C0 + g.C1;
+    const uint32_t S = (uint32_t)g.D * g.H * g.W;            // host checks B * S * max(C) < 2^31
+    const uint32_t nbricks = (uint32_t)g.B * nbz * nby * nbx;
+    const int tx = warp % 3, rg = warp / 3;
+    const bool want_bias = dbias != nullptr && blockIdx.y == 0;
+    // thread offsets of the fragment elements: A (row = ci, col = position), B (k = position, n = co)
+    const int xoff = (tq + tx) * XS + gq;
+    const int doff = NCDHW ? tq + gq * PS8 : tq * DS + gq;
+
+    float acc[3][3][2][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) acc[a][b][c][d] = 0.f;
+    if (tid < 8) bsum[tid] = 0.f;
+    float bacc[3] = {0.f, 0.f, 0.f};
+
+    auto stage = [&](uint32_t brick, int buf) {
+        uint32_t t = brick;
+        const int bx = (int)(t % (uint32_t)nbx); t /= (uint32_t)nbx;
+        const int by = (int)(t % (uint32_t)nby); t /= (uint32_t)nby;
+        const int bz = (int)(t % (uint32_t)nbz);
+        const uint32_t b = t / (uint32_t)nbz;
+        const int z0 = bz * MB_Z, y0 = by * MB_Y, x0c = bx * MB_X;
+        const uint32_t pb = b * S;                            // first position of this batch element
+        float* Xs = msm + buf * M8_STAGE;
+        float* dYs = Xs + M_NH * XS;
+#pragma unroll
+        for (int i = 0; i < (M_NH * 8 + M8_THREADS - 1) / M8_THREADS; ++i) {
+            const int idx = tid + i * M8_THREADS;
+            if (idx < M_NH * 8) {
+                const int hp = idx >> 3, c4 = (idx & 7) * 4;
+                const int hx = hp % MH_X, hyz = hp / MH_X, hy = hyz % MH_Y, hz = hyz / MH_Y;
+                const int z = z0 + hz - 1, yy = y0 + hy - 1, x = x0c + hx - 1;
+                const int c = c0 + c4;
+                const bool ok = (unsigned)z < (unsigned)g.D && (unsigned)yy < (unsigned)g.H && (unsigned)x < (unsigned)g.W && c < Cin;
+                const uint32_t row = pb + ((uint32_t)z * g.H + yy) * g.W + x;
+                const float* src = !ok ? x0 : (c < g.C0 ? x0 + (size_t)(row * (uint32_t)g.C0 + c) : x1 + (size_t)(row * (uint32_t)g.C1 + (c - g.C0)));
+                cp_async16(Xs + hp * XS + c4, src, ok);
+            }
+        }
+        if (tid < 256) {
+            if (NCDHW) {
+                // [o][lz][ly][8 x] <- dy[b][o][z][y][x0c .. x0c+7]: two 16-byte pieces per (o, row)
+                const int pc = tid & 1, rr = (tid >> 1) & 15, o = tid >> 5;
+                const int lz = rr >> 2, ly = rr & 3;
+                const int z = z0 + lz, yy = y0 + ly, x = x0c + pc * 4;
+                const bool ok = o < g.Co && z < g.D && yy < g.H && x < g.W;       // W % 4 == 0: a piece is all in or all out
+                const float* src = ok ? dy + (size_t)((b * (uint32_t)g.Co + o) * S + ((uint32_t)z * g.H + yy) * g.W + x) : dy;
+                cp_async16(dYs + o * PS8 + rr * 8 + pc * 4, src, ok);
+            } else {
+                // [pos][8 co] <- dy[b][z][y][x][0..7]
+                const int pc = tid & 1, pos = tid >> 1;
+                const int lx = pos % MB_X, ly = (pos / MB_X) % MB_Y, lz = pos / (MB_X * MB_Y);
+                const int z = z0 + lz, yy = y0 + ly, x = x0c + lx;
+                const bool ok = z < g.D && yy < g.H && x < g.W;
+                const float* src = ok ? dy + (size_t)((pb + ((uint32_t)z * g.H + yy) * g.W + x) * 8u + pc * 4) : dy;
+                cp_async16(dYs + pos * DS + pc * 4, src, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int it = 0;
+    if (blockIdx.x < nbricks) stage(blockIdx.x, 0);
+    for (uint32_t brick = blockIdx.x; brick < nbricks; brick += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const bool more = brick + gridDim.x < nbricks;
+        if (more) stage(brick + gridDim.x, buf ^ 1);       // the other buffer was released by the sync that ended brick it-1
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const float* Xs = msm + buf * M8_STAGE;
+        const float* dYs = Xs + M_NH * XS;
+        if (want_bias) {
+            // element idx of the 8 x 128 dy tile: co = idx / 128 (NCDHW tile) or idx % 8 (channels-last tile)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int idx = tid + i * M8_THREADS;
+                if (idx < 1024) bacc[i] += NCDHW ? dYs[(idx >> 7) * PS8 + (idx & 127)] : dYs[(idx >> 3) * DS + (idx & 7)];
+            }
+        }
+        const float* xt = Xs + xoff;
+        const float* dt = dYs + doff;
+        if (rg == 0) bw8_rows<0, NCDHW>(xt, dt, acc);       // warp-uniform
+        else if (rg == 1) bw8_rows<1, NCDHW>(xt, dt, acc);
+        else if (rg == 2) bw8_rows<2, NCDHW>(xt, dt, acc);
+        else bw8_rows<3, NCDHW>(xt, dt, acc);
+        __syncthreads();                                      // buffer `buf` may be restaged by the next iteration's prefetch
+    }
+    // ---- reduce the four row groups in shared memory ([27][32 ci][8 co], stage 0 is dead), then one atomic pass
+    float* Wsm = msm;
+    for (int r = 0; r < 4; ++r) {
+        if (rg == r) {
+#pragma unroll
+            for (int tz = 0; tz < 3; ++tz)
+#pragma unroll
+                for (int ty = 0; ty < 3; ++ty) {
+                    const int tap = (tz * 3 + ty) * 3 + tx;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int cl = mt * 16 + gq + (q >> 1) * 8;
+                            const int co = 2 * tq + (q & 1);
+                            float* w = Wsm + (tap * 32 + cl) * 8 + co;
+                            *w = r == 0 ? acc[tz][ty][mt][q] : *w + acc[tz][ty][mt][q];
+                        }
+                }
+        }
+        __syncthreads();
+    }
+    const int nci = min(32, Cin - c0);
+    for (int idx = tid; idx < 27 * 32 * 8; idx += M8_THREADS) {
+        const int co = idx & 7, cl = (idx >> 3) & 31, tap = idx >> 8;
+        const float v = Wsm[idx];
+        if (cl < nci && co < g.Co && v != 0.f) {
+            if (native) atomicAdd(&dWt[((int64_t)co * Cin + c0 + cl) * 27 + tap], v);
+            else atomicAdd(&dWt[((int64_t)tap * Cin + c0 + cl) * g.Co + co], v);
+        }
+    }
+    if (want_bias) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int idx = tid + i * M8_THREADS;
+            if (idx < 1024) {
+                const int o = NCDHW ? idx >> 7 : idx & 7;
+                if (o < g.Co) atomicAdd(&bsum[o], bacc[i]);
+            }
+        }
+        __syncthreads();
+        if (tid < g.Co) atomicAdd(&dbias[tid], bsum[tid]);
+    }
+}
+
 }  // namespace
 
 int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* x1, int C1, float* dWt, float* dbias,
@@ -261,6 +463,31 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
     // even out the bricks per CTA
     const int64_t per = ceil_div64(nbricks, gx);
     gx = ceil_div64(nbricks, per);
+    // Co = 8 with 16-byte-addressable dy rows: the row-reuse kernel (one persistent CTA per SM and channel chunk)
+    static const bool old8 = []() { const char* e = getenv("MICFORMER_CONV_BW8_OLD"); return e && e[0] == '1'; }();
+    const int cmax = C0 > C1 ? C0 : C1;
+    if (Co == 8 && !old8 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (!dy_ncdhw || (W & 3) == 0) &&
+        (int64_t)B * D * H * W * (cmax > 8 ? cmax : 8) < ((int64_t)1 << 31) && nbricks < ((int64_t)1 << 31)) {
+        int64_t g8 = ceil_div64((int64_t)num_sms(), chunks);
+        if (g8 > nbricks) g8 = nbricks;
+        if (g8 < 1) g8 = 1;
+        const int64_t per8 = ceil_div64(nbricks, g8);
+        g8 = ceil_div64(nbricks, per8);
+        const size_t smem8 = (2 * M8_STAGE + 16) * sizeof(float);
+        static bool once8 = false;
+        if (!once8) {
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            once8 = true;
+        }
+        if (dy_ncdhw)
+            mic::launch(conv3_mma_bwd_weight8_kernel<true>, dim3((unsigned)g8, chunks), dim3(M8_THREADS), smem8, st, dy, x0, x1, dWt, dbias,
+                        g, nbz, nby, nbx, native);
+        else
+            mic::launch(conv3_mma_bwd_weight8_kernel<false>, dim3((unsigned)g8, chunks), dim3(M8_THREADS), smem8, st, dy, x0, x1, dWt, dbias,
+                        g, nbz, nby, nbx, native);
+        return check_launch("conv3_mma_bwd_weight8_kernel");
+    }
     dim3 grid((unsigned)gx, chunks);
     const size_t smem = (M_NH * XS + M_NB * DS + 16) * sizeof(float);
     if (Co == 8) {
