@@ -266,21 +266,23 @@ __device__ __forceinline__ uint32_t rn_tf32_bits(float x) { return (__float_as_u
 // The nine halo rows RG, RG + 4, .. of one warp, fully unrolled: (hz, hy), the valid (tz, ty) taps of each row and every
 // shared-memory offset are compile-time constants (the first version of this kernel computed them at run time and was
 // instruction-issue bound: ~350 instructions per row for 18 MMAs).  xt / dt already carry the thread's fragment offsets.
-template <int RG, bool NCDHW>
-__device__ __forceinline__ void bw8_rows(const float* __restrict__ xt, const float* __restrict__ dt, float (&acc)[3][3][2][4]) {
-    constexpr int sp = NCDHW ? 1 : DS;
+// MT 16-channel tiles x NT 8-output tiles per tap, MT * NT = 2: (2, 1) for Co <= 8, (1, 2) for Co <= 16.
+template <int RG, bool NCDHW, int MT, int NT>
+__device__ __forceinline__ void bw8_rows(const float* __restrict__ xt, const float* __restrict__ dt, float (&acc)[3][3][MT][NT][4]) {
+    constexpr int XSx = MT == 2 ? XS : 24;       // x row stride: 8 tq + gq / 24 tq + gq are both conflict-free
+    constexpr int sp = NCDHW ? 1 : DS, so = NCDHW ? PS8 : 1;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         const int ir = RG + 4 * i;
         const int hz = ir / MH_Y, hy = ir % MH_Y;
-        const float* xr = xt + (hz * MH_Y + hy) * MH_X * XS;
-        uint32_t xa[2][2][2];
+        const float* xr = xt + (hz * MH_Y + hy) * MH_X * XSx;
+        uint32_t xa[MT][2][2];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 xa[mt][hh][0] = rn_tf32_bits(xr[mt * 16 + hh * 8]);
-                xa[mt][hh][1] = rn_tf32_bits(xr[4 * XS + mt * 16 + hh * 8]);
+                xa[mt][hh][1] = rn_tf32_bits(xr[4 * XSx + mt * 16 + hh * 8]);
             }
 #pragma unroll
         for (int tz = 0; tz < 3; ++tz)
@@ -289,45 +291,54 @@ __device__ __forceinline__ void bw8_rows(const float* __restrict__ xt, const flo
                 const int lz = hz - tz, ly = hy - ty;
                 if (lz >= 0 && lz < MB_Z && ly >= 0 && ly < MB_Y) {
                     const float* db = dt + (lz * MB_Y + ly) * 8 * sp;
-                    const uint32_t b0 = rn_tf32_bits(db[0]), b1 = rn_tf32_bits(db[4 * sp]);
-                    mma_tf32(acc[tz][ty][0], xa[0][0][0], xa[0][1][0], xa[0][0][1], xa[0][1][1], b0, b1);
-                    mma_tf32(acc[tz][ty][1], xa[1][0][0], xa[1][1][0], xa[1][0][1], xa[1][1][1], b0, b1);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint32_t b0 = rn_tf32_bits(db[nt * 8 * so]), b1 = rn_tf32_bits(db[4 * sp + nt * 8 * so]);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            mma_tf32(acc[tz][ty][mt][nt], xa[mt][0][0], xa[mt][1][0], xa[mt][0][1], xa[mt][1][1], b0, b1);
+                    }
                 }
             }
     }
 }
 
-template <bool NCDHW>
+template <bool NCDHW, int MT, int NT>
 __global__ void __launch_bounds__(M8_THREADS, 1)
 conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restrict__ x0, const float* __restrict__ x1,
                              float* __restrict__ dWt, float* __restrict__ dbias, MGeom g, int nbz, int nby, int nbx,
                              int native) {
     pdl_sync();
+    constexpr int CH = 16 * MT, COP = 8 * NT;    // input channels per CTA chunk, padded output channels
+    constexpr int XSx = MT == 2 ? XS : 24;
+    constexpr int NB = (128 * COP + M8_THREADS - 1) / M8_THREADS;
     extern __shared__ __align__(16) float msm[];
-    float* bsum = msm + 2 * M8_STAGE;            // [8]
+    float* bsum = msm + 2 * M8_STAGE;            // [16]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
-    const int c0 = blockIdx.y * 32;
+    const int c0 = blockIdx.y * CH;
     const int Cin = g.C0 + g.C1;
     const uint32_t S = (uint32_t)g.D * g.H * g.W;            // host checks B * S * max(C) < 2^31
     const uint32_t nbricks = (uint32_t)g.B * nbz * nby * nbx;
     const int tx = warp % 3, rg = warp / 3;
     const bool want_bias = dbias != nullptr && blockIdx.y == 0;
     // thread offsets of the fragment elements: A (row = ci, col = position), B (k = position, n = co)
-    const int xoff = (tq + tx) * XS + gq;
+    const int xoff = (tq + tx) * XSx + gq;
     const int doff = NCDHW ? tq + gq * PS8 : tq * DS + gq;
 
-    float acc[3][3][2][4];
+    float acc[3][3][MT][NT][4];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b)
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < MT * NT; ++c)
 #pragma unroll
-                for (int d = 0; d < 4; ++d) acc[a][b][c][d] = 0.f;
-    if (tid < 8) bsum[tid] = 0.f;
-    float bacc[3] = {0.f, 0.f, 0.f};
+                for (int d = 0; d < 4; ++d) (&acc[a][b][0][0][0])[c * 4 + d] = 0.f;
+    if (tid < 16) bsum[tid] = 0.f;
+    float bacc[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bacc[i] = 0.f;
 
     auto stage = [&](uint32_t brick, int buf) {
         uint32_t t = brick;
@@ -339,36 +350,40 @@ conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restri
         const uint32_t pb = b * S;                            // first position of this batch element
         float* Xs = msm + buf * M8_STAGE;
         float* dYs = Xs + M_NH * XS;
+        constexpr int PCS = CH / 4;                           // 16-byte pieces per position
 #pragma unroll
-        for (int i = 0; i < (M_NH * 8 + M8_THREADS - 1) / M8_THREADS; ++i) {
+        for (int i = 0; i < (M_NH * PCS + M8_THREADS - 1) / M8_THREADS; ++i) {
             const int idx = tid + i * M8_THREADS;
-            if (idx < M_NH * 8) {
-                const int hp = idx >> 3, c4 = (idx & 7) * 4;
+            if (idx < M_NH * PCS) {
+                const int hp = idx / PCS, c4 = (idx % PCS) * 4;
                 const int hx = hp % MH_X, hyz = hp / MH_X, hy = hyz % MH_Y, hz = hyz / MH_Y;
                 const int z = z0 + hz - 1, yy = y0 + hy - 1, x = x0c + hx - 1;
                 const int c = c0 + c4;
                 const bool ok = (unsigned)z < (unsigned)g.D && (unsigned)yy < (unsigned)g.H && (unsigned)x < (unsigned)g.W && c < Cin;
                 const uint32_t row = pb + ((uint32_t)z * g.H + yy) * g.W + x;
                 const float* src = !ok ? x0 : (c < g.C0 ? x0 + (size_t)(row * (uint32_t)g.C0 + c) : x1 + (size_t)(row * (uint32_t)g.C1 + (c - g.C0)));
-                cp_async16(Xs + hp * XS + c4, src, ok);
+                cp_async16(Xs + hp * XSx + c4, src, ok);
             }
         }
-        if (tid < 256) {
-            if (NCDHW) {
-                // [o][lz][ly][8 x] <- dy[b][o][z][y][x0c .. x0c+7]: two 16-byte pieces per (o, row)
-                const int pc = tid & 1, rr = (tid >> 1) & 15, o = tid >> 5;
+        if (NCDHW) {
+            // [o][lz][ly][8 x] <- dy[b][o][z][y][x0c .. x0c+7]: two 16-byte pieces per (o, row)
+            for (int idx = tid; idx < COP * 32; idx += M8_THREADS) {
+                const int pc = idx & 1, rr = (idx >> 1) & 15, o = idx >> 5;
                 const int lz = rr >> 2, ly = rr & 3;
                 const int z = z0 + lz, yy = y0 + ly, x = x0c + pc * 4;
                 const bool ok = o < g.Co && z < g.D && yy < g.H && x < g.W;       // W % 4 == 0: a piece is all in or all out
                 const float* src = ok ? dy + (size_t)((b * (uint32_t)g.Co + o) * S + ((uint32_t)z * g.H + yy) * g.W + x) : dy;
                 cp_async16(dYs + o * PS8 + rr * 8 + pc * 4, src, ok);
-            } else {
-                // [pos][8 co] <- dy[b][z][y][x][0..7]
-                const int pc = tid & 1, pos = tid >> 1;
+            }
+        } else {
+            // [pos][COP co] <- dy[b][z][y][x][0 .. COP-1]   (Co == COP)
+            constexpr int PD = COP / 4;
+            for (int idx = tid; idx < 128 * PD; idx += M8_THREADS) {
+                const int pc = idx % PD, pos = idx / PD;
                 const int lx = pos % MB_X, ly = (pos / MB_X) % MB_Y, lz = pos / (MB_X * MB_Y);
                 const int z = z0 + lz, yy = y0 + ly, x = x0c + lx;
                 const bool ok = z < g.D && yy < g.H && x < g.W;
-                const float* src = ok ? dy + (size_t)((pb + ((uint32_t)z * g.H + yy) * g.W + x) * 8u + pc * 4) : dy;
+                const float* src = ok ? dy + (size_t)((pb + ((uint32_t)z * g.H + yy) * g.W + x) * (uint32_t)COP + pc * 4) : dy;
                 cp_async16(dYs + pos * DS + pc * 4, src, ok);
             }
         }
@@ -387,22 +402,22 @@ conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restri
         const float* Xs = msm + buf * M8_STAGE;
         const float* dYs = Xs + M_NH * XS;
         if (want_bias) {
-            // element idx of the 8 x 128 dy tile: co = idx / 128 (NCDHW tile) or idx % 8 (channels-last tile)
+            // element idx of the COP x 128 dy tile: co = idx / 128 (NCDHW tile) or idx % COP (channels-last tile)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < NB; ++i) {
                 const int idx = tid + i * M8_THREADS;
-                if (idx < 1024) bacc[i] += NCDHW ? dYs[(idx >> 7) * PS8 + (idx & 127)] : dYs[(idx >> 3) * DS + (idx & 7)];
+                if (idx < 128 * COP) bacc[i] += NCDHW ? dYs[(idx >> 7) * PS8 + (idx & 127)] : dYs[(idx / COP) * DS + (idx % COP)];
             }
         }
         const float* xt = Xs + xoff;
         const float* dt = dYs + doff;
-        if (rg == 0) bw8_rows<0, NCDHW>(xt, dt, acc);       // warp-uniform
-        else if (rg == 1) bw8_rows<1, NCDHW>(xt, dt, acc);
-        else if (rg == 2) bw8_rows<2, NCDHW>(xt, dt, acc);
-        else bw8_rows<3, NCDHW>(xt, dt, acc);
+        if (rg == 0) bw8_rows<0, NCDHW, MT, NT>(xt, dt, acc);       // warp-uniform
+        else if (rg == 1) bw8_rows<1, NCDHW, MT, NT>(xt, dt, acc);
+        else if (rg == 2) bw8_rows<2, NCDHW, MT, NT>(xt, dt, acc);
+        else bw8_rows<3, NCDHW, MT, NT>(xt, dt, acc);
         __syncthreads();                                      // buffer `buf` may be restaged by the next iteration's prefetch
     }
-    // ---- reduce the four row groups in shared memory ([27][32 ci][8 co], stage 0 is dead), then one atomic pass
+    // ---- reduce the four row groups in shared memory ([27][CH ci][COP co], stage 0 is dead), then one atomic pass
     float* Wsm = msm;
     for (int r = 0; r < 4; ++r) {
         if (rg == r) {
@@ -412,21 +427,23 @@ conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restri
                 for (int ty = 0; ty < 3; ++ty) {
                     const int tap = (tz * 3 + ty) * 3 + tx;
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int cl = mt * 16 + gq + (q >> 1) * 8;
-                            const int co = 2 * tq + (q & 1);
-                            float* w = Wsm + (tap * 32 + cl) * 8 + co;
-                            *w = r == 0 ? acc[tz][ty][mt][q] : *w + acc[tz][ty][mt][q];
-                        }
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int cl = mt * 16 + gq + (q >> 1) * 8;
+                                const int co = nt * 8 + 2 * tq + (q & 1);
+                                float* w = Wsm + (tap * CH + cl) * COP + co;
+                                *w = r == 0 ? acc[tz][ty][mt][nt][q] : *w + acc[tz][ty][mt][nt][q];
+                            }
                 }
         }
         __syncthreads();
     }
-    const int nci = min(32, Cin - c0);
-    for (int idx = tid; idx < 27 * 32 * 8; idx += M8_THREADS) {
-        const int co = idx & 7, cl = (idx >> 3) & 31, tap = idx >> 8;
+    const int nci = min(CH, Cin - c0);
+    for (int idx = tid; idx < 27 * CH * COP; idx += M8_THREADS) {
+        const int co = idx % COP, cl = (idx / COP) % CH, tap = idx / (COP * CH);
         const float v = Wsm[idx];
         if (cl < nci && co < g.Co && v != 0.f) {
             if (native) atomicAdd(&dWt[((int64_t)co * Cin + c0 + cl) * 27 + tap], v);
@@ -435,10 +452,10 @@ conv3_mma_bwd_weight8_kernel(const float* __restrict__ dy, const float* __restri
     }
     if (want_bias) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NB; ++i) {
             const int idx = tid + i * M8_THREADS;
-            if (idx < 1024) {
-                const int o = NCDHW ? idx >> 7 : idx & 7;
+            if (idx < 128 * COP) {
+                const int o = NCDHW ? idx >> 7 : idx % COP;
                 if (o < g.Co) atomicAdd(&bsum[o], bacc[i]);
             }
         }
@@ -465,10 +482,17 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
     gx = ceil_div64(nbricks, per);
     // Co = 8 with 16-byte-addressable dy rows: the row-reuse kernel (one persistent CTA per SM and channel chunk)
     static const bool old8 = []() { const char* e = getenv("MICFORMER_CONV_BW8_OLD"); return e && e[0] == '1'; }();
+    // the row-reuse kernel: dy rows must be 16-byte addressable (channels-last: Co == 8 or 16 exactly)
     const int cmax = C0 > C1 ? C0 : C1;
-    if (Co == 8 && !old8 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (!dy_ncdhw || (W & 3) == 0) &&
-        (int64_t)B * D * H * W * (cmax > 8 ? cmax : 8) < ((int64_t)1 << 31) && nbricks < ((int64_t)1 << 31)) {
-        int64_t g8 = ceil_div64((int64_t)num_sms(), chunks);
+    // Co = 16 (conv_offset): measured no faster than the kernel above (stage 0: 102 vs 82 us, step time equal, gpurun r2bk) --
+    // six 16-channel chunk CTAs re-stage the dy tile -- so it is opt-in there (MICFORMER_CONV_BW16_NEW=1)
+    static const bool old16 = []() { const char* e = getenv("MICFORMER_CONV_BW16_NEW"); return !(e && e[0] == '1'); }();
+    const bool dy_ok = (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (dy_ncdhw ? (W & 3) == 0 : true);
+    if (dy_ok && !(Co == 8 ? old8 : old16) && (int64_t)B * D * H * W * (cmax > 16 ? cmax : 16) < ((int64_t)1 << 31) &&
+        nbricks < ((int64_t)1 << 31)) {
+        const int ch = Co == 8 ? 32 : 16;
+        const int chunks8 = ceil_div(C0 + C1, ch);
+        int64_t g8 = ceil_div64((int64_t)num_sms(), chunks8);
         if (g8 > nbricks) g8 = nbricks;
         if (g8 < 1) g8 = 1;
         const int64_t per8 = ceil_div64(nbricks, g8);
@@ -476,16 +500,18 @@ int mma_conv3_bwd_weight(const float* dy, const float* x0, int C0, const float* 
         const size_t smem8 = (2 * M8_STAGE + 16) * sizeof(float);
         static bool once8 = false;
         if (!once8) {
-            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<true, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(conv3_mma_bwd_weight8_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
             once8 = true;
         }
-        if (dy_ncdhw)
-            mic::launch(conv3_mma_bwd_weight8_kernel<true>, dim3((unsigned)g8, chunks), dim3(M8_THREADS), smem8, st, dy, x0, x1, dWt, dbias,
-                        g, nbz, nby, nbx, native);
-        else
-            mic::launch(conv3_mma_bwd_weight8_kernel<false>, dim3((unsigned)g8, chunks), dim3(M8_THREADS), smem8, st, dy, x0, x1, dWt, dbias,
-                        g, nbz, nby, nbx, native);
+        const dim3 grid8((unsigned)g8, chunks8);
+#define LAUNCH8(NC, MT_, NT_) mic::launch(conv3_mma_bwd_weight8_kernel<NC, MT_, NT_>, grid8, dim3(M8_THREADS), smem8, st, dy, x0, x1, dWt, \
+                                         dbias, g, nbz, nby, nbx, native)
+        if (Co == 8) { if (dy_ncdhw) LAUNCH8(true, 2, 1); else LAUNCH8(false, 2, 1); }
+        else { if (dy_ncdhw) LAUNCH8(true, 1, 2); else LAUNCH8(false, 1, 2); }
+#undef LAUNCH8
         return check_launch("conv3_mma_bwd_weight8_kernel");
     }
     dim3 grid((unsigned)gx, chunks);
