@@ -52,6 +52,11 @@ ops.ln_bwd(dy, x, None, n1w, mean, rstd, dxn, None, (B, D, D, D))
 
 # ---- BASELINE config 4: 4096 windows x 343 tokens x 96 channels x 3 heads
 qkv = r(4096 * 343, 3 * 96)
-ops.window_attn_fwd(qkv, 96, 3, 4096, (7, 7, 7), (7, 7, 7))
+o_a, lse_a = ops.window_attn_fwd(qkv, 96, 3, 4096, (7, 7, 7), (7, 7, 7))
+# ---- the same shape's tcgen05 backward
+ops.window_attn_bwd(qkv, o_a, r(4096 * 343, 96), lse_a, 96, 3, 4096, (7, 7, 7), (7, 7, 7))
+# ---- out_conv weight gradient (row-reuse mma.sync kernel): 2 x 128^3, 24 -> 8 classes, NCDHW dlogits
+dwo = torch.zeros(27, 24, 8, device="cuda"); dbo = torch.zeros(8, device="cuda")
+ops.conv3_bwd_weight(r(2, 8, 128, 128, 128), r(2, 128, 128, 128, 24), None, dwo, dbo, 2, (128, 128, 128), 8, True)
 torch.cuda.synchronize()
 print("done")
