@@ -75,6 +75,16 @@ int mic_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int 
 int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int w_is_kn,
                           float* db, int M, int N, int K, const float* rowscale, int rows_per_sample, void* stream);
 
+/* Decoder tail without the 4^3 block permutation (reverse_patch_embedding, reference models/MICFormer_self.py:1033-1037):
+ * the NEXT mic_linear_fwd / mic_linear_bwd_data / mic_linear_bwd_weight call of this host thread addresses its Y / dY
+ * matrix -- logically (B*dc*hc*wc cells) x (64*ch) ConvTranspose3d(k4,s4) rows, ld = 64*ch -- directly in the
+ * (B, 4dc, 4hc, 4wc, ch) channels-last grid it is the block permutation of (5-D TMA tensor maps; no intermediate, no
+ * mic_block_permute pass).  Tensor-core mode only, wc == 32, hc % 4 == 0, ch % 8 == 0; a call that cannot honour the view
+ * fails with MIC_ERR_UNSUPPORTED (it never silently treats the buffer as a plain matrix).  In mic_linear_bwd_weight
+ * (w_is_kn = 1 only) db receives the column sums of the buffer as laid out in memory: exact after summing the 64 block
+ * positions of a channel, i.e. for a bias tiled over the block positions.  (0,0,0,0) cancels a pending view. */
+int mic_linear_unpatch_view(int ch, int dc, int hc, int wc);
+
 /* ---- Windowed multi-head attention core: window_partition + softmax(q k^T * scale) v + window_reverse
  *      (:37-50,:117-132,:193-200,:251-258) without materialising windows or scores.  q/k/v/out are token-grid
  *      tensors (B,Dp,Hp,Wp,heads*hd) with row strides ldq/ldkv/ldo (k and v usually point into one kv buffer);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mic_linear_fwd": [P, I, P, I, I, P, P, I, I, I, I, I, P, I, P, I, P, I, I, P],
     "mic_linear_bwd_data": [P, I, P, I, I, P, I, I, I, I, P, I, P, I, I, P],
     "mic_linear_bwd_weight": [P, I, P, I, P, I, I, P, I, I, I, P, I, P],
+    "mic_linear_unpatch_view": [I, I, I, I],
     "mic_window_attn_fwd": [P, I, P, P, I, P, I, P, I, I, I, I, I, I, I, I, I, F, P],
     "mic_window_attn_bwd": [P, I, P, P, I, P, P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, I, F, P],
     "mic_conv3_fwd": [P, I, P, I, P, P, P, I, I, I, I, I, I, I, I, I, P],
@@ -87,6 +88,13 @@ def load() -> C.CDLL:
         if lib.mic_set_gemm_mode(int(mode)) != 0:
             raise RuntimeError(f"MICFORMER_GEMM_MODE={mode}: " + lib.mic_last_error_string().decode())
     return lib
+
+
+def unpatch_view(ch: int, dc: int, hc: int, wc: int) -> None:
+    """The next mic_linear_* call of this thread addresses its Y / dY matrix through the fine channels-last grid
+    (include/micformer_b200.h: mic_linear_unpatch_view)."""
+    if load().mic_linear_unpatch_view(ch, dc, hc, wc) != 0:
+        raise RuntimeError("mic_linear_unpatch_view: " + last_error())
 
 
 def last_error() -> str:

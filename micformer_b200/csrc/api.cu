@@ -33,6 +33,8 @@ int tc_linear_bwd_data(const float*, int, const float*, int, int, float*, int, i
                        const float*, int, int, int, cudaStream_t);
 int tc_linear_bwd_weight(const float*, int, const float*, int, float*, int, int, float*, int, int, int, const float*, int, int,
                          cudaStream_t);
+bool tc_view_pending();
+void tc_view_set(int ch, int dc, int hc, int wc);
 // window_attn_tc.cu (tcgen05; large windows, head_dim 32)
 int tc_window_attn_fwd(const float*, int, const float*, const float*, int, float*, int, float*, int, int, int, int, int, int,
                        int, int, int, float, cudaStream_t);
@@ -86,6 +88,7 @@ extern "C" int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
                               const float* rowscale, int rows_per_sample, int accumulate, void* stream) {
     MIC_REQUIRE(X && W && Y && M > 0 && N > 0 && K > 0, "linear_fwd: bad arguments (M=%d N=%d K=%d)", M, N, K);
     MIC_REQUIRE(!(accumulate && (act || res)), "linear_fwd: accumulate cannot be combined with act/res");
+    const bool view_was_pending = tc_view_pending();
     const int mode = g_gemm_mode.load();
     if (mode == 1) {
         int rc = tc_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
@@ -93,6 +96,7 @@ extern "C" int mic_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
         warn_fallback("mic_linear_fwd", M, N, K);
     }
+    if (view_was_pending) { tc_view_set(0, 0, 0, 0); return fail(MIC_ERR_UNSUPPORTED, "mic_linear_fwd: the unpatch view needs the tensor-core path (gemm mode 1) and a 32-cell-wide grid"); }
     return simt_linear_fwd(X, ldx, W, ldw, w_is_kn, bias, Y, ldy, M, N, K, act, pre, ldpre, res, ldres, rowscale,
                            rows_per_sample, accumulate, (cudaStream_t)stream);
 }
@@ -101,6 +105,7 @@ extern "C" int mic_linear_bwd_data(const float* dY, int lddy, const float* W, in
                                    int M, int N, int K, const float* gelu_pre, int ldpre, const float* rowscale,
                                    int rows_per_sample, int accumulate, void* stream) {
     MIC_REQUIRE(dY && W && dX && M > 0 && N > 0 && K > 0, "linear_bwd_data: bad arguments");
+    const bool view_was_pending = tc_view_pending();
     const int mode = g_gemm_mode.load();
     if (mode == 1) {
         int rc = tc_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
@@ -108,6 +113,7 @@ extern "C" int mic_linear_bwd_data(const float* dY, int lddy, const float* W, in
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
         warn_fallback("mic_linear_bwd_data", M, N, K);
     }
+    if (view_was_pending) { tc_view_set(0, 0, 0, 0); return fail(MIC_ERR_UNSUPPORTED, "mic_linear_bwd_data: the unpatch view needs the tensor-core path (gemm mode 1) and a 32-cell-wide grid"); }
     return simt_linear_bwd_data(dY, lddy, W, ldw, w_is_kn, dX, lddx, M, N, K, gelu_pre, ldpre, rowscale, rows_per_sample,
                                 accumulate, (cudaStream_t)stream);
 }
@@ -116,6 +122,7 @@ extern "C" int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, 
                                      float* db, int M, int N, int K, const float* rowscale, int rows_per_sample,
                                      void* stream) {
     MIC_REQUIRE(dY && X && dW && M > 0 && N > 0 && K > 0, "linear_bwd_weight: bad arguments");
+    const bool view_was_pending = tc_view_pending();
     const int mode = g_gemm_mode.load();
     if (mode == 1) {
         int rc = tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample, mode,
@@ -123,8 +130,15 @@ extern "C" int mic_linear_bwd_weight(const float* dY, int lddy, const float* X, 
         if (rc != MIC_ERR_UNSUPPORTED) return rc;
         warn_fallback("mic_linear_bwd_weight", M, N, K);
     }
+    if (view_was_pending) { tc_view_set(0, 0, 0, 0); return fail(MIC_ERR_UNSUPPORTED, "mic_linear_bwd_weight: the unpatch view needs the tensor-core path (gemm mode 1) and a 32-cell-wide grid"); }
     return simt_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, w_is_kn, db, M, N, K, rowscale, rows_per_sample,
                                   (cudaStream_t)stream);
+}
+
+extern "C" int mic_linear_unpatch_view(int ch, int dc, int hc, int wc) {
+    MIC_REQUIRE(ch >= 0 && dc >= 0 && hc >= 0 && wc >= 0, "linear_unpatch_view: negative geometry");
+    tc_view_set(ch, dc, hc, wc);
+    return MIC_OK;
 }
 
 extern "C" int mic_window_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo,

@@ -52,7 +52,25 @@ struct TcEpi {
     int nst;                                // pipeline stages in use (3, or 2 when split3 doubles the tiles)
     float* db;                              // weight-gradient GEMMs (A = dY^T, MN-major): db[i] += sum_r A(i, r), folded into the
                                             // operand pass of the CTAs with blockIdx.y == 0 (one-shot kernel only)
+    // "unpatch view" (decoder tail): one operand is the (T cells) x (64 * ch) matrix of ConvTranspose3d(k4, s4) rows, but it
+    // LIVES as the (B, 4 dc, 4 hc, 4 wc, ch) channels-last grid it is the 4^3-block permutation of.  Its tensor map is 5-D
+    // {cc = 4 ch, wc, 4 (y sub-position), hc, B * dc * 4} and (column, row) of the logical matrix become the coordinates
+    // below -- the block_permute pass (0.22 ms each way at 128^3) disappears.  vw_op: 0 off, 1 C (store), 2 A K-major
+    // (rows = cells), 3 B MN-major (32 columns x 32 cells per box)
+    int vw_op, vw_cc, vw_wc, vw_hc;
 };
+
+// (column, row) of the logical rows matrix -> 5-D coordinates of the fine grid (see TcEpi::vw_op)
+__device__ __forceinline__ void view_coords(const TcEpi& e, int col, int row, int (&c)[5]) {
+    const int g = col / e.vw_cc;
+    c[0] = col - g * e.vw_cc;               // (x sub-position, channel)
+    c[2] = g & 3;                           // y sub-position
+    const int r1 = row / e.vw_wc;
+    c[1] = row - r1 * e.vw_wc;              // cell x
+    const int bd = r1 / e.vw_hc;
+    c[3] = r1 - bd * e.vw_hc;               // cell y
+    c[4] = bd * 4 + (g >> 2);               // (batch, cell z, z sub-position)
+}
 
 // optional per-CTA phase trace (debug): 16 x u64 globaltimer stamps per CTA when a buffer is registered
 __device__ unsigned long long* g_tc_trace = nullptr;
@@ -98,6 +116,28 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, const int (&c)[5]) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, const int (&c)[5]) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+// operand / output tile moves that honour the unpatch view
+__device__ __forceinline__ void load_a_k(void* dst, const CUtensorMap* map, uint64_t* bar, const TcEpi& e, int r0, int i0) {
+    if (e.vw_op == 2) { int c[5]; view_coords(e, r0, i0, c); tma_load_5d(dst, map, bar, c); }
+    else tma_load_2d(dst, map, bar, r0, i0);
+}
+__device__ __forceinline__ void load_b_mn(void* dst, const CUtensorMap* map, uint64_t* bar, const TcEpi& e, int j, int r0) {
+    if (e.vw_op == 3) { int c[5]; view_coords(e, j, r0, c); tma_load_5d(dst, map, bar, c); }
+    else tma_load_2d(dst, map, bar, j, r0);
+}
+__device__ __forceinline__ void store_c(const CUtensorMap* map, const void* src, const TcEpi& e, int gj0, int i0) {
+    if (e.vw_op == 1) { int c[5]; view_coords(e, gj0, i0, c); tma_store_5d(map, src, c); }
+    else tma_store_2d(map, src, gj0, i0);
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -240,10 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int g = 0; g < TM / 32; ++g) tma_load_2d(a + g * 4096, &mapA, &full[s], i0 + g * 32, r0);
                 } else {
-                    tma_load_2d(a, &mapA, &full[s], r0, i0);
+                    load_a_k(a, &mapA, &full[s], e, r0, i0);
                 }
                 if (B_MN) {
-                    for (int g = 0; g < b_groups; ++g) tma_load_2d(b + g * 4096, &mapB, &full[s], j0 + g * 32, r0);
+                    for (int g = 0; g < b_groups; ++g) load_b_mn(b + g * 4096, &mapB, &full[s], e, j0 + g * 32, r0);
                 } else {
                     tma_load_2d(b, &mapB, &full[s], r0, j0);
                 }
@@ -507,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && lane == 0 && ncol > 0) {
                 if (EPI == 4 || EPI == 5) tma_reduce_add_2d(&mapC, cbuf, gj0, i0);
-                else tma_store_2d(&mapC, cbuf, gj0, i0);
+                else store_c(&mapC, cbuf, e, gj0, i0);
                 if (want_pre) tma_store_2d(&mapP, pbuf, gj0, i0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -613,10 +653,10 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                         for (int g = 0; g < TM / 32; ++g) tma_load_2d(a + g * 4096, &mapA, &full[s], i0 + g * 32, r0);
                     } else {
-                        tma_load_2d(a, &mapA, &full[s], r0, i0);
+                        load_a_k(a, &mapA, &full[s], e, r0, i0);
                     }
                     if (B_MN) {
-                        for (int g = 0; g < b_groups; ++g) tma_load_2d(b + g * 4096, &mapB, &full[s], j0 + g * 32, r0);
+                        for (int g = 0; g < b_groups; ++g) load_b_mn(b + g * 4096, &mapB, &full[s], e, j0 + g * 32, r0);
                     } else {
                         tma_load_2d(b, &mapB, &full[s], r0, j0);
                     }
@@ -800,7 +840,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (elected) {
                     if (ncol > 0) {
                         if (EPI == 4 || EPI == 5) tma_reduce_add_2d(&mapC, cbuf, gj0, i0);
-                        else tma_store_2d(&mapC, cbuf, gj0, i0);
+                        else store_c(&mapC, cbuf, e, gj0, i0);
                         if (want_pre) tma_store_2d(&mapP, pbuf, gj0, i0);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -852,6 +892,35 @@ static bool make_map(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1
     return r == CUDA_SUCCESS;
 }
 
+// 5-D fp32 tensor map of the unpatch view (TcEpi::vw_op): dims {cc, wc, 4, hc, Z}; box = 32 columns x `rows_w` cells x
+// `rows_h` cell rows
+static bool make_view_map(CUtensorMap* m, const float* base, int cc, int wc, int hc, int64_t Z, uint32_t rows_w, uint32_t rows_h,
+                          bool atom32) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[5] = {(cuuint64_t)cc, (cuuint64_t)wc, 4, (cuuint64_t)hc, (cuuint64_t)Z};
+    cuuint64_t strides[4] = {(cuuint64_t)cc * 4, (cuuint64_t)cc * 4 * wc, (cuuint64_t)cc * 4 * wc * 4, (cuuint64_t)cc * 4 * wc * 4 * hc};
+    cuuint32_t box[5] = {32, rows_w, 1, rows_h, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// the view requested for the NEXT mic_linear_* call of this host thread (mic_linear_unpatch_view); consumed by that call
+struct UnpatchView { int ch, dc, hc, wc; };
+static thread_local UnpatchView g_view = {0, 0, 0, 0};
+bool tc_view_pending() { return g_view.ch != 0; }
+void tc_view_set(int ch, int dc, int hc, int wc) { g_view = {ch, dc, hc, wc}; }
+static UnpatchView take_view() { UnpatchView v = g_view; g_view = {0, 0, 0, 0}; return v; }
+// rows = cells, cols = 64 * ch of the logical matrix; the kernels move 128-row / 32-row boxes, so a box must be 4 / 1 whole
+// cell rows
+static bool view_ok(const UnpatchView& v, int rows, int cols) {
+    return v.ch > 0 && v.ch % 8 == 0 && v.wc == 32 && v.hc % 4 == 0 && v.dc > 0 && cols == 64 * v.ch &&
+           rows % (v.dc * v.hc * v.wc) == 0 && rows % 128 == 0;
+}
+
 struct TcOperand {
     const float* p;
     bool mn_major;     // true: output index contiguous, rows = reduction index
@@ -893,6 +962,14 @@ static int tc_gemm(const TcOperand& A, const TcOperand& B, TcEpi e, int R, int k
     ok = ok && make_map(&mC, e.C, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldc, 32, TM, false);
     if (ok && epi == 1 && e.pre) ok = make_map(&mP, e.pre, (uint64_t)J, (uint64_t)I, (uint64_t)e.ldpre, 32, TM, false);
     else mP = mC;
+    if (ok && e.vw_op) {
+        // the viewed operand: (cells) x (64 ch) logical matrix stored as the fine channels-last grid
+        const int64_t cells = e.vw_op == 1 ? I : (e.vw_op == 2 ? I : R);
+        const int64_t Z = cells / ((int64_t)e.vw_hc * e.vw_wc) * 4;
+        if (e.vw_op == 1) ok = epi == 0 && make_view_map(&mC, e.C, e.vw_cc, e.vw_wc, e.vw_hc, Z, 32, 4, false);
+        else if (e.vw_op == 2) ok = !A.mn_major && make_view_map(&mA, A.p, e.vw_cc, e.vw_wc, e.vw_hc, Z, 32, 4, false);
+        else ok = B.mn_major && make_view_map(&mB, B.p, e.vw_cc, e.vw_wc, e.vw_hc, Z, 32, 1, true);
+    }
     if (!ok) return MIC_ERR_UNSUPPORTED;
     e.nst = STAGES;
     if (e.split3) e.round_rn = 1;
@@ -994,8 +1071,11 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
                   int M, int N, int K, int act, float* pre, int ldpre, const float* res, int ldres, const float* rowscale,
                   int rps, int accumulate, int mode, cudaStream_t st) {
     (void)mode;
+    const UnpatchView vw = take_view();
     if (N < 16 || K < 8) return MIC_ERR_UNSUPPORTED;
+    if (vw.ch && (!view_ok(vw, M, N) || act || pre || res || accumulate || rowscale)) return MIC_ERR_UNSUPPORTED;
     TcEpi e{};
+    if (vw.ch) { e.vw_op = 1; e.vw_cc = 4 * vw.ch; e.vw_wc = vw.wc; e.vw_hc = vw.hc; }
     e.C = Y; e.ldc = ldy; e.I = M; e.J = N; e.bias = bias; e.act = act; e.pre = pre; e.ldpre = ldpre; e.res = res;
     e.ldres = ldres; e.rowscale_i = rowscale; e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
     // forward GEMMs carry the logits parity bar (1e-3 vs the fp32 CPU path): 3xTF32 split keeps them fp32-faithful
@@ -1015,7 +1095,7 @@ int tc_linear_fwd(const float* X, int ldx, const float* W, int ldw, int w_is_kn,
     // by the CTA's shared-memory bandwidth): split the reduction over blockIdx.z.  The output is initialised with the residual
     // (or zero) by a copy node and every split adds rowscale * (partial [+ bias in split 0]) with TMA reduce-add.
     static const bool splitk = []() { const char* v = getenv("MICFORMER_FWD_SPLITK"); return !(v && v[0] == '0'); }();
-    if (splitk && !act && !accumulate && !pre && M > 0) {
+    if (splitk && !act && !accumulate && !pre && M > 0 && !vw.ch) {
         const int kb_total = (K + TKB - 1) / TKB;
         int bnt = N <= 128 ? ((N + 15) / 16) * 16 : 128;
         if (N > 128) { const int nt = (N + 127) / 128; bnt = (((N + nt - 1) / nt) + 31) / 32 * 32; }
@@ -1039,8 +1119,11 @@ int tc_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int w
                        int K, const float* gelu_pre, int ldpre, const float* rowscale, int rps, int accumulate, int mode,
                        cudaStream_t st) {
     (void)mode;
+    const UnpatchView vw = take_view();
     if (K < 16 || N < 8) return MIC_ERR_UNSUPPORTED;
+    if (vw.ch && !view_ok(vw, M, N)) return MIC_ERR_UNSUPPORTED;
     TcEpi e{};
+    if (vw.ch) { e.vw_op = 2; e.vw_cc = 4 * vw.ch; e.vw_wc = vw.wc; e.vw_hc = vw.hc; }     // dY is the viewed operand
     e.C = dX; e.ldc = lddx; e.I = M; e.J = K; e.mulgrad = gelu_pre; e.ldmg = ldpre; e.rowscale_i = rowscale;
     e.rps_i = rps > 0 ? rps : 1; e.accumulate = accumulate ? 1 : 0;
     TcOperand A{dY, false, lddy};
@@ -1052,8 +1135,14 @@ int tc_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, int w
 int tc_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int w_is_kn, float* db,
                          int M, int N, int K, const float* rowscale, int rps, int mode, cudaStream_t st) {
     (void)mode;
+    const UnpatchView vw = take_view();
     if (N < 16 || K < 16) return MIC_ERR_UNSUPPORTED;
+    // dY viewed: only as the MN-major B operand (w_is_kn).  db then receives the column sums of the buffer AS LAID OUT IN
+    // MEMORY (rows of 64 ch floats): the sums over the 64 block positions of each channel are exact, which is all a bias
+    // tiled over the block positions (br.repeat(64)) needs
+    if (vw.ch && (!view_ok(vw, M, N) || !w_is_kn || rowscale)) return MIC_ERR_UNSUPPORTED;
     TcEpi e{};
+    if (vw.ch) { e.vw_op = 3; e.vw_cc = 4 * vw.ch; e.vw_wc = vw.wc; e.vw_hc = vw.hc; }
     e.C = dW; e.ldc = lddw; e.accumulate = 2;
     TcOperand A{}, B{};
     if (!w_is_kn) { A = {dY, true, lddy}; B = {X, true, ldx}; e.I = N; e.J = K; }

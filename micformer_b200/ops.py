@@ -236,12 +236,14 @@ def _view_ptr(t: Tensor, col: int) -> int:
 def linear_fwd(X: Tensor, ldx: int, W: Tensor, bias: Optional[Tensor], M: int, Nout: int, K: int, *, out: Tensor = None,
                out_col: int = 0, ldy: int = None, w_is_kn: bool = False, ldw: int = None, w_col: int = 0, x_col: int = 0,
                act: bool = False, pre: Tensor = None, res: Tensor = None, rowscale: Tensor = None, rps: int = 0,
-               accumulate: bool = False):
+               accumulate: bool = False, view=None):
     if out is None:
         out = _empty((M, Nout), X)
         ldy = Nout
     if ldw is None:
         ldw = Nout if w_is_kn else K
+    if view is not None:
+        N.unpatch_view(*view)          # Y lives as the fine channels-last grid (decoder tail)
     N.call("mic_linear_fwd", _view_ptr(X, x_col), ldx, _view_ptr(W, w_col), ldw, int(w_is_kn), N.ptr(bias),
            _view_ptr(out, out_col), ldy, M, Nout, K, int(act), N.ptr(pre), Nout, N.ptr(res), Nout, N.ptr(rowscale), rps,
            int(accumulate))
@@ -250,12 +252,14 @@ def linear_fwd(X: Tensor, ldx: int, W: Tensor, bias: Optional[Tensor], M: int, N
 
 def linear_bwd_data(dY: Tensor, lddy: int, W: Tensor, M: int, Nout: int, K: int, *, dy_col: int = 0, out: Tensor = None,
                     out_col: int = 0, lddx: int = None, w_is_kn: bool = False, ldw: int = None, w_col: int = 0,
-                    gelu_pre: Tensor = None, rowscale: Tensor = None, rps: int = 0, accumulate: bool = False):
+                    gelu_pre: Tensor = None, rowscale: Tensor = None, rps: int = 0, accumulate: bool = False, view=None):
     if out is None:
         out = _empty((M, K), dY)
         lddx = K
     if ldw is None:
         ldw = Nout if w_is_kn else K
+    if view is not None:
+        N.unpatch_view(*view)          # dY lives as the fine channels-last grid (decoder tail)
     N.call("mic_linear_bwd_data", _view_ptr(dY, dy_col), lddy, _view_ptr(W, w_col), ldw, int(w_is_kn),
            _view_ptr(out, out_col), lddx, M, Nout, K, N.ptr(gelu_pre), K, N.ptr(rowscale), rps, int(accumulate))
     return out
@@ -263,13 +267,16 @@ def linear_bwd_data(dY: Tensor, lddy: int, W: Tensor, M: int, Nout: int, K: int,
 
 def linear_bwd_weight(dY: Tensor, lddy: int, X: Tensor, ldx: int, M: int, Nout: int, K: int, *, dy_col: int = 0,
                       x_col: int = 0, w_is_kn: bool = False, dW: Tensor = None, lddw: int = None, dw_col: int = 0,
-                      want_bias: bool = True, db: Tensor = None, rowscale: Tensor = None, rps: int = 0):
-    """Returns (dW, db); dW/db are accumulated into when passed in."""
+                      want_bias: bool = True, db: Tensor = None, rowscale: Tensor = None, rps: int = 0, view=None):
+    """Returns (dW, db); dW/db are accumulated into when passed in.  ``view``: dY lives as the fine channels-last grid
+    (decoder tail); db is then exact only after summing the 64 block positions of a channel (see the header)."""
     if dW is None:
         dW = _zeros((K, Nout) if w_is_kn else (Nout, K), dY)
         lddw = Nout if w_is_kn else K
     if db is None and want_bias:
         db = _zeros((Nout,), dY)
+    if view is not None:
+        N.unpatch_view(*view)
     N.call("mic_linear_bwd_weight", _view_ptr(dY, dy_col), lddy, _view_ptr(X, x_col), ldx, _view_ptr(dW, dw_col), lddw,
            int(w_is_kn), N.ptr(db) if want_bias else None, M, Nout, K, N.ptr(rowscale), rps)
     return dW, db
@@ -977,6 +984,16 @@ class UnpatchFn(torch.autograd.Function):
         return dxm, dxf, dn2w, dn2b, dwr, dbr64
 
 
+_TAIL_VIEW = _os.environ.get("MICFORMER_TAIL_VIEW", "1") != "0"
+
+
+def _tail_view(D: int, H: int, W: int, Ch: int, T: int):
+    """(ch, dc, hc, wc) when the tail GEMMs can address the fine grid directly (mic_linear_unpatch_view), else None."""
+    if _TAIL_VIEW and N.get_gemm_mode() == 1 and W == 32 and H % 4 == 0 and Ch % 8 == 0 and T % 128 == 0:
+        return (Ch, D, H, W)
+    return None
+
+
 class SegHeadFn(torch.autograd.Function):
     """Decoder tail (reference M:1033-1037 + Head M:1053): cat[moving, fixed] -> norm2 -> ConvTranspose3d(2E->E/2,k4,s4)
     -> Conv3d(E/2->num_classes,k3,p1), NCDHW logits.  wr: (2E, 64*E/2) permuted (kz,ky,kx,co); br64: bias tiled 64x;
@@ -994,11 +1011,16 @@ class SegHeadFn(torch.autograd.Function):
         _mode = N.get_gemm_mode()
         if "gemm" in _dbg:
             N.set_gemm_mode(0)
-        rows = linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True)
-        N.set_gemm_mode(_mode)
         y24 = _empty((B, 4 * D, 4 * H, 4 * W, Ch), xm)
-        block_permute(rows, y24, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
-        del rows
+        view = _tail_view(D, H, W, Ch, T)
+        if view is not None:
+            # the GEMM's TMA stores scatter the ConvTranspose rows straight into the fine grid: no rows buffer, no permute pass
+            linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True, out=y24, ldy=64 * Ch, view=view)
+        else:
+            rows = linear_fwd(xn, 2 * E, wr, br64, T, 64 * Ch, 2 * E, w_is_kn=True)
+            block_permute(rows, y24, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
+            del rows
+        N.set_gemm_mode(_mode)
         logits = _empty((B, NC, 4 * D, 4 * H, 4 * W), xm)
         if "conv" in _dbg:
             N.set_gemm_mode(0)
@@ -1025,11 +1047,15 @@ class SegHeadFn(torch.autograd.Function):
             sb.run(conv3_bwd_weight, dlog, y24, None, dwo, dbo, B, (4 * D, 4 * H, 4 * W), NC, True)
             dy24 = torch.empty_like(y24)
             conv3_bwd_data(dlog, wo, dy24, False, None, False, B, (4 * D, 4 * H, 4 * W), NC, True)
-            drows = _empty((T, 64 * Ch), xm)
-            block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
+            view = _tail_view(D, H, W, Ch, T)
+            if view is not None:
+                drows = dy24           # the GEMMs read the fine grid through 5-D tensor maps
+            else:
+                drows = _empty((T, 64 * Ch), xm)
+                block_permute(dy24, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
             del dy24
-            dwr, dbr64 = linear_bwd_weight_side(sb, drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True)
-            dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True)
+            dwr, dbr64 = linear_bwd_weight_side(sb, drows, 64 * Ch, xn, 2 * E, T, 64 * Ch, 2 * E, w_is_kn=True, view=view)
+            dxn = linear_bwd_data(drows, 64 * Ch, wr, T, 64 * Ch, 2 * E, w_is_kn=True, view=view)
             dxm, dxf, dn2w, dn2b = ln_bwd(dxn, xm, xf, n2w, mean, rstd, None, None, (B, D, H, W), beta=n2b)
         return dxm, dxf, dn2w, dn2b, dwr, dbr64, dwo, None, _gret(bo, dbo)
 
