@@ -205,3 +205,39 @@ def test_tc_conv3_fwd_bwd(tc_mode, C0, C1, Co, dims, ncdhw):
     ops.conv3_bwd_weight(dy, x0d, x1d, dwt, dbias, B, (D, H, W), Co, ncdhw)
     dw_ref = w.grad.permute(2, 3, 4, 1, 0).reshape(27, Cin, Co)
     assert rel_err(dwt.cpu(), dw_ref) < 2e-3 and rel_err(dbias.cpu(), b.grad) < 1e-4
+
+
+def test_unpatch_view_tail_gemms(tc_mode):
+    """mic_linear_unpatch_view: the decoder tail's GEMMs address the (B, 4D, 4H, 4W, ch) grid directly (5-D TMA maps) --
+    same numbers as GEMM + mic_block_permute (reference M:1033-1037), forward and both backward GEMMs; a grid that is not
+    32 cells wide is refused loudly instead of being read as a plain matrix."""
+    from micformer_b200 import ops
+    B, D, H, W, Ch, K = 1, 2, 4, 32, 8, 48
+    T = B * D * H * W
+    Nout = 64 * Ch
+    x = _rand(T, K, seed=1).to(DEV); w = (_rand(K, Nout, seed=2) * 0.2).to(DEV); b = _rand(Nout, seed=3).to(DEV)
+    view = (Ch, D, H, W)
+    # forward: rows -> permute  vs  direct
+    rows = ops.linear_fwd(x, K, w, b, T, Nout, K, w_is_kn=True)
+    fine_ref = torch.empty(B, 4 * D, 4 * H, 4 * W, Ch, device=DEV)
+    ops.block_permute(rows, fine_ref, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, False)
+    fine = torch.full_like(fine_ref, 7.0)
+    ops.linear_fwd(x, K, w, b, T, Nout, K, w_is_kn=True, out=fine, ldy=Nout, view=view)
+    assert torch.equal(fine, fine_ref)
+    # backward: dY given on the fine grid
+    dfine = _rand(B, 4 * D, 4 * H, 4 * W, Ch, seed=4).to(DEV)
+    drows = torch.empty(T, Nout, device=DEV)
+    ops.block_permute(dfine, drows, B, D, H, W, 4, Ch, 64 * D * H * W * Ch, True)
+    dx_ref = ops.linear_bwd_data(drows, Nout, w, T, Nout, K, w_is_kn=True)
+    dx = ops.linear_bwd_data(dfine, Nout, w, T, Nout, K, w_is_kn=True, view=view)
+    assert max_rel(dx.cpu(), dx_ref.cpu().double()) < 1e-6
+    dw_ref, db_ref = ops.linear_bwd_weight(drows, Nout, x, K, T, Nout, K, w_is_kn=True)
+    dw, db = ops.linear_bwd_weight(dfine, Nout, x, K, T, Nout, K, w_is_kn=True, view=view)
+    assert max_rel(dw.cpu(), dw_ref.cpu().double()) < 1e-5
+    # db: exact after summing the 64 block positions of a channel (a bias tiled over the block positions)
+    assert max_rel(db.view(64, Ch).sum(0).cpu(), db_ref.view(64, Ch).sum(0).cpu().double()) < 1e-5
+    # 16 cells wide: refused, and the pending view does not leak into the next call
+    with pytest.raises(RuntimeError):
+        ops.linear_fwd(x[:T // 2], K, w, b, T // 2, Nout, K, w_is_kn=True, out=fine, ldy=Nout, view=(Ch, D, H, 16))
+    rows2 = ops.linear_fwd(x, K, w, b, T, Nout, K, w_is_kn=True)
+    assert torch.equal(rows2, rows)
