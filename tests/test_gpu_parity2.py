@@ -123,8 +123,9 @@ def test_w7_forward_backward_tensor_core_mode():
 
 
 def test_config4_attention_4096_windows():
-    """BASELINE config 4 at full size (4096 windows x 343 tokens x 96 channels x 3 heads): the tcgen05 kernel against fp64
-    softmax attention on a sample of windows spread over the whole grid (first, last, CTA-boundary and random ones)"""
+    """BASELINE config 4 at full size (4096 windows x 343 tokens x 96 channels x 3 heads): the tcgen05 forward AND backward
+    kernels against fp64 softmax attention / its autograd on a sample of windows spread over the whole grid (first, last,
+    CTA-boundary and random ones)"""
     from micformer_b200 import _native as N, ops
     prev = N.get_gemm_mode()
     N.set_gemm_mode(1)
@@ -132,18 +133,30 @@ def test_config4_attention_4096_windows():
         Bw, C, heads, hd = 4096, 96, 3, 32
         g = torch.Generator().manual_seed(4)
         qkv = torch.randn(Bw * 343, 3 * C, generator=g)
-        o, lse = ops.window_attn_fwd(qkv.cuda(), C, heads, Bw, (7, 7, 7), (7, 7, 7))
-        o, lse = o.cpu(), lse.cpu()
+        qd = qkv.cuda()
+        o_d, lse_d = ops.window_attn_fwd(qd, C, heads, Bw, (7, 7, 7), (7, 7, 7))
+        # the tcgen05 backward at the same size (12288 CTAs, one per window and head): gradients of sum(o * do)
+        do = torch.randn(Bw * 343, C, generator=g)
+        dqkv = ops.window_attn_bwd(qd, o_d, do.cuda(), lse_d, C, heads, Bw, (7, 7, 7), (7, 7, 7)).cpu()
+        o, lse = o_d.cpu(), lse_d.cpu()
+        assert bool(torch.isfinite(dqkv).all())
         pick = sorted(set([0, 1, 147, 148, 149, 2047, 4094, 4095] + torch.randint(0, Bw, (24,), generator=g).tolist()))
         for w in pick:
-            blk = qkv[w * 343:(w + 1) * 343].double()
+            blk = qkv[w * 343:(w + 1) * 343].double().requires_grad_(True)
+            tot = 0.0
             for h in range(heads):
                 q, k, v = (blk[:, i * C + h * hd:i * C + (h + 1) * hd] for i in range(3))
                 s = (q * hd ** -0.5) @ k.t()
                 ref = s.softmax(-1) @ v
+                tot = tot + (ref * do[w * 343:(w + 1) * 343, h * hd:(h + 1) * hd].double()).sum()
                 got = o[w * 343:(w + 1) * 343, h * hd:(h + 1) * hd].double()
-                assert float((got - ref).abs().max() / ref.abs().max()) < 3e-3, (w, h)
-                assert float((lse[w * 343:(w + 1) * 343, h].double() - torch.logsumexp(s, -1)).abs().max()) < 3e-3
+                assert float((got - ref.detach()).abs().max() / ref.detach().abs().max()) < 3e-3, (w, h)
+                assert float((lse[w * 343:(w + 1) * 343, h].double() - torch.logsumexp(s.detach(), -1)).abs().max()) < 3e-3
+            tot.backward()
+            gw = dqkv[w * 343:(w + 1) * 343].double()
+            for i in range(3):           # dq, dk, dv column blocks
+                a, b = gw[:, i * C:(i + 1) * C], blk.grad[:, i * C:(i + 1) * C]
+                assert float((a - b).abs().max() / b.abs().max()) < 5e-3, (w, i)
     finally:
         N.set_gemm_mode(prev)
 
